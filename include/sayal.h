@@ -1,0 +1,187 @@
+/*
+ * sayal.h — C ABI of the B200-native OpenSayal step path.
+ *
+ * The reference (gopmur/OpenSayal) has no FFI: its de-facto boundary is the public surface of
+ * `class Fluid` (inc/fluid.cuh:15-116) as used by main (src/main.cu:49,97) and by the renderer
+ * (src/graphics_handler.cu:269-283).  Every entry point below names the reference interface it
+ * replaces.  Plain pointers and sizes only; no C++/torch types.  All functions return 0 on success
+ * or a negative SAYAL_E* code (the reference never checks an error and calls exit(); we never do).
+ *
+ * Field layout handed across this boundary is the reference's: row-major W x H, flipped y,
+ *     index(i, j) = (H - 1 - j) * W + i          (src/fluid.cu:163-165)
+ * fp32 for U/V/P/SMOKE, int32 for IS_SOLID/TOTAL_S.
+ *
+ * Threading contract: one host thread per sayal_sim; distinct sims are independent.
+ */
+#ifndef SAYAL_H
+#define SAYAL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAYAL_ABI_VERSION 1
+
+/* error codes */
+#define SAYAL_OK 0
+#define SAYAL_EINVAL (-1)   /* bad argument / unsupported configuration */
+#define SAYAL_ECUDA (-2)    /* a CUDA call failed; see sayal_last_error() */
+#define SAYAL_EIO (-3)      /* config file missing / unreadable */
+#define SAYAL_EPARSE (-4)   /* config file is not valid JSON / wrong value type */
+#define SAYAL_ENOMEM (-5)
+
+/* fields, for sayal_get_field / sayal_set_field / sayal_device_ptr */
+enum sayal_field {
+  SAYAL_U = 0,        /* Fluid::d_vel_x   (fluid.cuh:65) */
+  SAYAL_V = 1,        /* Fluid::d_vel_y   (fluid.cuh:66) */
+  SAYAL_P = 2,        /* Fluid::d_pressure (fluid.cuh:64) */
+  SAYAL_SMOKE = 3,    /* Fluid::d_smoke   (fluid.cuh:67) */
+  SAYAL_IS_SOLID = 4, /* Fluid::d_is_solid (fluid.cuh:71), int32 0/1 */
+  SAYAL_TOTAL_S = 5,  /* Fluid::d_total_s  (fluid.cuh:72), int32 0..4 */
+  SAYAL_FIELD_COUNT = 6
+};
+
+/*
+ * The simulation subset of the reference's `Config` (inc/config_parser.hpp:9-114) — exactly the
+ * members the Fluid constructor and init_device_memory read (src/fluid.cu:41-61, 111-124), with the
+ * defaults of src/config_parser.cpp:21-119.  JSON key in the trailing comment.
+ */
+typedef struct sayal_config {
+  int32_t width;            /* sim.width             (1920) */
+  int32_t height;           /* sim.height            (1080) */
+  float cell_size;          /* sim.cell_size         (1.0; Fluid stores it as int, fluid.cuh:46) */
+  int32_t enable_drain;     /* sim.enable_drain      (true) */
+  int32_t enable_pressure;  /* sim.enable_pressure   (false) */
+  int32_t enable_smoke;     /* sim.enable_smoke      (true) */
+  int32_t enable_interactive; /* sim.enable_interactive (false) — carried, unused headless */
+  int32_t proj_n;           /* sim.projection.n      (50) */
+  float proj_o;             /* sim.projection.o      (1.9) */
+  int32_t wt_pipe_height;   /* sim.wind_tunnel.pipe_height  (height/4) */
+  int32_t wt_pipe_length;   /* hard-coded 0 in config_parser.cpp:64 */
+  int32_t wt_smoke_length;  /* sim.wind_tunnel.smoke_length (1) */
+  int32_t wt_smoke_height;  /* sim.wind_tunnel.smoke_height (height/4) */
+  int32_t wt_smoke_count;   /* sim.wind_tunnel.smoke_count  (1) */
+  float wt_speed;           /* sim.wind_tunnel.speed (0) */
+  float wt_smoke;           /* sim.wind_tunnel.smoke (1) */
+  float g;                  /* sim.physics.g         (0) */
+  float d_t;                /* sim.time.d_t          (0.05) */
+  int32_t enable_real_time; /* sim.time.enable_real_time (false) — carried for the caller */
+  float real_time_multiplier; /* sim.time.real_time_multiplier (1) */
+  int32_t smoke_enable_decay; /* sim.smoke.enable_decay (false) */
+  float smoke_decay_rate;   /* sim.smoke.decay_rate  (0.05) */
+  int32_t obstacle_enable;  /* sim.obstacle.enable   (true) */
+  int32_t obstacle_center_x; /* sim.obstacle.center_x (width/2) */
+  int32_t obstacle_center_y; /* sim.obstacle.center_y (height/2) */
+  float obstacle_radius;    /* sim.obstacle.radius   (min(width,height)/30) */
+  float density;            /* fluid.density         (1) */
+  float drag_coeff;         /* fluid.drag_coeff      (0) */
+  float viscosity;          /* fluid.viscosity       (0.001 in the reference) */
+  int32_t block_size_x;     /* thread.cuda.block_size_x (64) — carried for the reference shim only */
+  int32_t block_size_y;     /* thread.cuda.block_size_y (1) */
+} sayal_config;
+
+/* struct Source (inc/fluid.cuh:8-13): the mouse impulse passed by value to Fluid::update. */
+typedef struct sayal_source {
+  int32_t active;
+  float smoke;
+  float velocity;
+  int32_t x; /* position.x, cell units */
+  int32_t y; /* position.y, cell units, j (bottom-up) */
+} sayal_source;
+
+/*
+ * Optional y-slab description for multi-GPU runs (no reference equivalent).  A slab owns
+ * the memory rows [row0, row0+rows) of a global_height-row domain and carries `halo` ghost rows on each
+ * interior side.  All-zero / NULL means "whole domain on this GPU".
+ */
+typedef struct sayal_slab {
+  int32_t global_height; /* H of the whole domain */
+  int32_t row0;          /* first owned memory row (memory row r = H-1-j) */
+  int32_t rows;          /* owned rows */
+  int32_t halo;          /* ghost rows kept above and below (clipped at the domain edge) */
+} sayal_slab;
+
+typedef struct sayal_sim sayal_sim;
+
+/* ---- configuration ------------------------------------------------------------------------- */
+/* Fill `cfg` with the reference defaults for a width x height grid (config_parser.cpp:21-119). */
+int sayal_config_defaults(int32_t width, int32_t height, sayal_config* cfg);
+/* ConfigParser::parse() (config_parser.cpp:15-185) incl. get_or's dotted/nested lookup
+ * (config_parser.hpp:131-151).  Missing keys take defaults; a missing file is SAYAL_EIO and invalid
+ * JSON SAYAL_EPARSE instead of the reference's uncaught exception. */
+int sayal_config_load(const char* json_path, sayal_config* cfg);
+int sayal_config_parse(const char* json_text, size_t len, sayal_config* cfg);
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* Fluid::Fluid(Config) (fluid.cu:41-71): allocate device state on `device`, build is_solid/total_s
+ * (fluid.cu:99-161), zero u, v, smoke (and p, which the reference leaves uninitialised). */
+int sayal_create(const sayal_config* cfg, int32_t device, sayal_sim** out);
+/* Same, for one y-slab of a larger domain. */
+int sayal_create_slab(const sayal_config* cfg, int32_t device, const sayal_slab* slab, sayal_sim** out);
+/* Fluid::~Fluid() (fluid.cu:73-84). */
+void sayal_destroy(sayal_sim* sim);
+
+/* ---- stepping ------------------------------------------------------------------------------ */
+/* Fluid::update(Source, d_t) (fluid.cu:770-795) without the trailing cudaDeviceSynchronize:
+ * enqueues one step on the sim's stream and returns.  `src` may be NULL (inactive source). */
+int sayal_step(sayal_sim* sim, const sayal_source* src, float d_t);
+/* Headless batch: `steps` updates with an inactive source (CUDA-graph replay). */
+int sayal_run(sayal_sim* sim, int32_t steps, float d_t);
+/* The cudaDeviceSynchronize() of fluid.cu:794, restricted to this sim's stream. */
+int sayal_sync(sayal_sim* sim);
+
+/* ---- state access -------------------------------------------------------------------------- */
+/* Copy a whole field device->host / host->device in the reference layout (W*H elements of 4 bytes).
+ * For a slab sim the buffer holds the owned rows only (rows*W elements). Synchronous. */
+int sayal_get_field(sayal_sim* sim, int32_t field, void* host_dst);
+int sayal_set_field(sayal_sim* sim, int32_t field, const void* host_src);
+/* Zero-copy view for a renderer (replaces dereferencing Fluid::d_* on device,
+ * graphics_handler.cu:269-283): device pointer to memory row 0 of the local array, its pitch in
+ * elements, the first global memory row it holds and the number of rows held (incl. ghost rows). */
+int sayal_device_ptr(sayal_sim* sim, int32_t field, void** dev_ptr, int64_t* pitch_elems,
+                     int32_t* first_row, int32_t* n_rows);
+/* Fluid::min_pressure / max_pressure (fluid.cuh:61-62, fluid.cu:778-787), of the last step.
+ * Synchronises the stream. Only meaningful when enable_pressure. */
+int sayal_pressure_range(sayal_sim* sim, float* min_p, float* max_p);
+/* Fluid::get_general_velocity(x, y) (fluid.cu:541-545) at `n` host-supplied points. */
+int sayal_sample_velocity(sayal_sim* sim, int32_t n, const float* xs, const float* ys, float* out_u,
+                          float* out_v);
+
+/* ---- staged access (tests, multi-GPU drivers) ----------------------------------------------- */
+/* Individual stages of Fluid::update on the sim's stream, in the reference's order
+ * (fluid.cu:771-793).  sayal_step == forces, [zero_pressure], projection(n), [pressure range],
+ * extrapolation, velocity advection, [smoke advection + decay]. */
+int sayal_stage_forces(sayal_sim* sim, const sayal_source* src, float d_t);
+int sayal_stage_zero_pressure(sayal_sim* sim);
+int sayal_stage_projection(sayal_sim* sim, int32_t iterations, float d_t);
+int sayal_stage_extrapolation(sayal_sim* sim);
+int sayal_stage_advect_velocity(sayal_sim* sim, float d_t);
+int sayal_stage_advect_smoke(sayal_sim* sim, float d_t);
+
+/* Tuning / introspection.  Known keys: "projection_kernel" (0 = plain half-sweeps, 1 = register-tile
+ * temporally blocked), "temporal_block" (iterations per pass), "use_graph" (0/1).  */
+int sayal_set_option(sayal_sim* sim, const char* key, int64_t value);
+int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value);
+/* Number of kernels this library has launched on behalf of `sim` since creation. */
+int64_t sayal_launch_count(sayal_sim* sim);
+/* CUDA stream of the sim (cudaStream_t as void*), for event timing by the caller. */
+void* sayal_stream(sayal_sim* sim);
+
+/* Slab runs: rows [row0-halo, row0) and [row0+rows, row0+rows+halo) are ghost rows.  These copy ghost /
+ * edge rows between the sim's device arrays and caller-provided DEVICE buffers (packed U then V then
+ * SMOKE, `nrows` rows of W floats each) on the sim's stream — the caller moves the buffers between GPUs
+ * (NCCL send/recv or peer copy).  side: 0 = low-row side (top of the picture), 1 = high-row side. */
+int sayal_slab_pack_edge(sayal_sim* sim, int32_t side, int32_t nrows, int32_t field_mask, void* dev_buf);
+int sayal_slab_unpack_ghost(sayal_sim* sim, int32_t side, int32_t nrows, int32_t field_mask,
+                            const void* dev_buf);
+
+const char* sayal_last_error(void);
+int sayal_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAYAL_H */
