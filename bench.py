@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py — the driver's measurement contract for the OpenSayal step path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+metric    cell-steps/s = (cells x steps) / device time, n = 50 SOR iterations per step (BASELINE.json)
+workload  N = 1: BASELINE configs[1] — 1920x1080 wind tunnel (speed 200, pipe_height 270), disc r=36, smoke
+          on, drain on, n=50, viscosity 0, synthetic initial fields.
+          N > 1: the same slab per GPU stacked in y (1920 x 1080*N), one process per GPU, ghost-row exchange
+          between neighbours ("weak" scaling).
+value     whole-job throughput, state resident in HBM, every step timed on its own with CUDA events on the
+          sim's stream and the L2 flushed (256 MiB write) between steps; max over ranks.
+e2e       the same job through the public API from pinned HOST buffers: upload u, v, smoke, K x step with a
+          host-side Source, download u, v, smoke — wall clock, copies inside the timed region.
+roofline  the dominant kernel (projection_tile_kernel): algorithmic bytes per launch / mean launch duration
+          (CUDA events around the projection stage), against MEASURED_PEAKS.json's HBM copy bandwidth.
+cpu_baseline  the CPU restatement (oracle/, "port") on one host core, bounded sample of the same workload.
+
+--impl reference: the reference's own implementation of the path.  OpenSayal has NO CPU path — its
+implementation is CUDA (src/fluid.cu) — so this arm runs oracle/_ref (the unmodified reference sources built
+for sm_100 with the reference's Release flags) on the same B200, same config, same timing protocol; if that
+library is unavailable it falls back to the CPU port on all host threads and says so.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+N_SOR = 50
+
+
+def algorithmic_bytes_per_cell_step(n, pressure, smoke, drag=False):
+    """B_alg of SURVEY.md §8d / BASELINE.md §3."""
+    return 8 + (8 if drag else 0) + n * (17 + 8 * pressure) + 17 + 17 * smoke
+
+
+def measured_hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.05):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.period = period
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def workload_config(n_gpus: int):
+    from opensayal_b200.synthetic import baseline_config
+    cfg = baseline_config(1)
+    if n_gpus > 1:  # the same slab per GPU, stacked in y
+        cfg = baseline_config(1, width=1920, height=1080 * n_gpus)
+        cfg["sim.wind_tunnel.pipe_height"] = 270 * n_gpus
+        cfg["sim.obstacle.radius"] = 36.0
+    return cfg
+
+
+def config_block(cfg, n_gpus, extra=None):
+    c = cfg.c
+    out = {"workload": f"{c.width}x{c.height} wind tunnel (speed {c.wt_speed:g}, pipe_height {c.wt_pipe_height}), "
+                       f"disc r={c.obstacle_radius:g} at ({c.obstacle_center_x},{c.obstacle_center_y}), smoke on, drain on, "
+                       f"n={c.proj_n}, o={c.proj_o:g}, d_t={c.d_t:g}, viscosity 0 — BASELINE configs[1]"
+                       + (f" per GPU, stacked in y over {n_gpus} slabs" if n_gpus > 1 else ""),
+           "grid": [c.width, c.height], "cells": c.width * c.height, "sor_iterations": c.proj_n,
+           "parallelism": "single GPU" if n_gpus == 1 else f"y-slabs x{n_gpus}, ghost-row exchange",
+           "l2": "flushed between timed steps (256 MiB write)",
+           "initial_fields": "synthetic_fields(seed=1234): sin/cos modes amplitude 40 + noise 5"}
+    if extra:
+        out.update(extra)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+def bench_ours_single(args):
+    import numpy as np
+    import torch
+
+    from opensayal_b200 import Fluid, Source
+    from opensayal_b200.synthetic import synthetic_fields
+
+    torch.cuda.set_device(0)
+    cfg = workload_config(1)
+    c = cfg.c
+    W, H = c.width, c.height
+    cells = W * H
+    u, v, sm = synthetic_fields(W, H)
+    sim = Fluid(cfg, device=0)
+    for name, a in (("u", u), ("v", v), ("smoke", sm)):
+        sim.set_field(name, a)
+    stream = torch.cuda.ExternalStream(sim.stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush.fill_(1)
+
+    sim.run(max(args.warmup, 3))
+    sim.sync()
+
+    # ---- device-resident throughput: every step timed on its own, L2 flushed in between
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches0 = sim.launch_count
+    with ClockSampler(0) as clocks:
+        for k in range(args.steps):
+            flush_l2()
+            starts[k].record(stream)
+            sim.run(1)
+            stops[k].record(stream)
+        sim.sync()
+    launches = sim.launch_count - launches0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    ms_per_step = sum(step_ms) / len(step_ms)
+    value = cells / (ms_per_step * 1e-3)
+
+    # ---- the same loop without flushing (steady-state simulation: state stays in L2), for information
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sim.run(args.steps)
+    e1.record(stream)
+    sim.sync()
+    warm_ms = e0.elapsed_time(e1) / args.steps
+
+    # ---- dominant kernel: the projection stage alone (passes x projection_tile_kernel)
+    n = c.proj_n
+    l0 = sim.launch_count
+    sim.stage_projection(n, c.d_t)
+    sim.sync()
+    passes = sim.launch_count - l0
+    pstarts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    pstops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush_l2()
+        pstarts[k].record(stream)
+        sim.stage_projection(n, c.d_t)
+        pstops[k].record(stream)
+    sim.sync()
+    proj_ms = sum(s.elapsed_time(e) for s, e in zip(pstarts, pstops)) / args.steps
+    launch_ms = proj_ms / passes
+    alg_bytes_launch = 17.0 * cells * n / passes  # 17 B per cell per iteration x iterations per launch
+    achieved = alg_bytes_launch / (launch_ms * 1e-3) / 1e9
+    peak, peak_src = measured_hbm_peak()
+    b_alg = algorithmic_bytes_per_cell_step(n, int(bool(c.enable_pressure)), int(bool(c.enable_smoke and c.wt_smoke != 0)))
+    roofline = {"bound": "hbm", "kernel": "projection_tile_kernel", "achieved": round(achieved, 1), "peak": peak,
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                "peak_source": peak_src, "launches_per_step": passes, "ms_per_launch": round(launch_ms, 5),
+                "algorithmic_bytes_per_launch": alg_bytes_launch,
+                "share_of_step": round(proj_ms / ms_per_step, 3),
+                "whole_step": {"algorithmic_bytes_per_cell_step": b_alg,
+                               "achieved_GBps": round(value * b_alg / 1e9, 1),
+                               "frac": round(value * b_alg / 1e9 / peak, 4)},
+                "note": "algorithmic bytes give no credit for temporal blocking (T iterations per HBM pass), so "
+                        "frac > 1 means fewer physical bytes than one pass per sweep; see DESIGN.md"}
+
+    # ---- end to end from pinned host buffers through the public API
+    pinned = {k: torch.empty((H, W), dtype=torch.float32).pin_memory() for k in ("u", "v", "smoke")}
+    for k, a in (("u", u), ("v", v), ("smoke", sm)):
+        pinned[k].numpy()[...] = a
+    out = {k: torch.empty((H, W), dtype=torch.float32).pin_memory() for k in ("u", "v", "smoke")}
+    import ctypes as C
+    from opensayal_b200 import _abi
+    lib = _abi.load()
+    src = Source()  # inactive, passed from the host every step like main.cu:97 does
+    sim.sync()
+    t0 = time.perf_counter()
+    for k in ("u", "v", "smoke"):
+        _abi.check(lib.sayal_set_field(sim._sim, _abi.FIELD_NAMES[k], C.c_void_p(pinned[k].data_ptr())))
+    for _ in range(args.steps):
+        sim.step_async(src, c.d_t)
+    for k in ("u", "v", "smoke"):
+        _abi.check(lib.sayal_get_field(sim._sim, _abi.FIELD_NAMES[k], C.c_void_p(out[k].data_ptr())))
+    t1 = time.perf_counter()
+    assert np.isfinite(out["u"].numpy()).all()
+    e2e_value = cells * args.steps / (t1 - t0)
+    field_bytes = 3 * cells * 4
+    e2e = {"value": e2e_value, "unit": "cell-steps/s", "h2d_bytes_per_step": field_bytes / args.steps + 20,
+           "d2h_bytes_per_step": field_bytes / args.steps,
+           "protocol": "set_field(u,v,smoke) from pinned host + K x sayal_step(host Source) + get_field(u,v,smoke), wall clock"}
+
+    cpu = cpu_baseline_port(cfg, threads=1, target_seconds=12.0)
+    line = {
+        "metric": "cell-steps/sec (n=50 SOR)", "value": value, "unit": "cell-steps/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_block(cfg, 1, {"temporal_block": sim.get_option("temporal_block") or 5,
+                                        "projection_kernel": sim.get_option("projection_kernel")}),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+        "clocks": clocks.summary(),
+        "steady_state_ms_per_step_l2_warm": warm_ms,
+        "stage_ms": {"projection": proj_ms},
+    }
+    sim.close()
+    return line
+
+
+def cpu_baseline_port(cfg, threads, target_seconds):
+    """The oracle ("port": CPU restatement of fluid.cu) on `threads` host cores, bounded sample."""
+    from opensayal_b200.synthetic import synthetic_fields
+    from oracle.oracle import OracleSim
+    c = cfg.c
+    u, v, sm = synthetic_fields(c.width, c.height)
+    o = OracleSim(c, threads=threads)
+    for name, a in (("u", u), ("v", v), ("smoke", sm)):
+        o.set_field(name, a)
+    t0 = time.perf_counter()
+    steps = 0
+    while True:
+        o.step(None, c.d_t)
+        steps += 1
+        if time.perf_counter() - t0 > target_seconds or steps >= 64:
+            break
+    dt = time.perf_counter() - t0
+    o.close()
+    return {"value": c.width * c.height * steps / dt, "unit": "cell-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{steps} full steps of the same {c.width}x{c.height} n={c.proj_n} workload, {dt:.1f} s, "
+                      f"host has {os.cpu_count()} cores"}
+
+
+# ----------------------------------------------------------------------------------------------------
+def bench_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return None
+    import torch
+    from oracle.oracle import REF_LIB, RefSim
+    from opensayal_b200.synthetic import synthetic_fields
+
+    cfg = workload_config(1)  # the reference is single-GPU (no multi-GPU code exists in it)
+    c = cfg.c
+    cells = c.width * c.height
+    warm = max(args.warmup, 3)
+    if REF_LIB.exists() and torch.cuda.is_available():
+        torch.cuda.set_device(0)
+        u, v, sm = synthetic_fields(c.width, c.height)
+        ref = RefSim(c, device=0)
+        for name, a in (("u", u), ("v", v), ("smoke", sm)):
+            ref.set_field(name, a)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        ref.run_timed(warm)
+        with ClockSampler(0) as clocks:
+            ms = []
+            for _ in range(args.steps):
+                flush.fill_(1)
+                torch.cuda.synchronize()
+                ms.append(ref.run_timed(1))
+        ms_per_step = sum(ms) / len(ms)
+        value = cells / (ms_per_step * 1e-3)
+        launches = 1 + 2 * c.proj_n + 1 + 2 + 3  # forces, 2n sweeps, extrapolation, 2 + 3 advection
+        line = {
+            "impl": "reference", "metric": "cell-steps/sec (n=50 SOR)", "value": value, "unit": "cell-steps/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_block(cfg, 1, {"reference_build": "oracle/_ref: /root/reference/src/fluid.cu + helper.cu unmodified, "
+                                            "-O3 --use_fast_math -rdc=true -gencode arch=compute_100,code=sm_100, block (64,1), "
+                                            "fluid.viscosity=0 (H1)"}),
+            "cpu_baseline": {"value": value, "unit": "cell-steps/s", "cores": 0, "kind": "reference",
+                             "sample": f"{args.steps} full steps; OpenSayal has no CPU path, its implementation of the "
+                                       "step is CUDA and ran on the same B200 (0 host cores on the data path)"},
+            "e2e": {"value": value, "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": launches * args.steps, "clocks": clocks.summary(),
+        }
+        ref.close()
+        return line
+    # fallback: CPU port with every host thread
+    from oracle.oracle import oracle_lib
+    threads = oracle_lib().oracle_max_threads()
+    cpu = cpu_baseline_port(cfg, threads=threads, target_seconds=20.0)
+    return {"impl": "reference", "metric": "cell-steps/sec (n=50 SOR)", "value": cpu["value"], "unit": "cell-steps/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": warm, "ms_per_step": cells / cpu["value"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_block(cfg, 1, {"note": "oracle/_ref unavailable: CPU port on all host threads"}),
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        line = bench_reference(args)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return 0
+    rank, world, local = dist_env()
+    if args.gpus > 1 or world > 1:
+        from opensayal_b200.slab import bench_slabs
+        line = bench_slabs(args, workload_config, config_block, ClockSampler, measured_hbm_peak,
+                           algorithmic_bytes_per_cell_step)
+    else:
+        line = bench_ours_single(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,155 @@
+"""ctypes binding of include/sayal.h.
+
+The shared library is the product: if it is missing, or was built without the CUDA kernels, importing a
+symbol fails loudly — there is no Python or CPU fallback for the step path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libsayal_b200.so"
+
+SAYAL_OK = 0
+SAYAL_EINVAL, SAYAL_ECUDA, SAYAL_EIO, SAYAL_EPARSE, SAYAL_ENOMEM = -1, -2, -3, -4, -5
+U, V, P, SMOKE, IS_SOLID, TOTAL_S = range(6)
+FIELD_NAMES = {"u": U, "v": V, "p": P, "smoke": SMOKE, "is_solid": IS_SOLID, "total_s": TOTAL_S}
+
+
+class SayalConfig(C.Structure):
+    """struct sayal_config — field order must match include/sayal.h."""
+
+    _fields_ = [
+        ("width", C.c_int32),
+        ("height", C.c_int32),
+        ("cell_size", C.c_float),
+        ("enable_drain", C.c_int32),
+        ("enable_pressure", C.c_int32),
+        ("enable_smoke", C.c_int32),
+        ("enable_interactive", C.c_int32),
+        ("proj_n", C.c_int32),
+        ("proj_o", C.c_float),
+        ("wt_pipe_height", C.c_int32),
+        ("wt_pipe_length", C.c_int32),
+        ("wt_smoke_length", C.c_int32),
+        ("wt_smoke_height", C.c_int32),
+        ("wt_smoke_count", C.c_int32),
+        ("wt_speed", C.c_float),
+        ("wt_smoke", C.c_float),
+        ("g", C.c_float),
+        ("d_t", C.c_float),
+        ("enable_real_time", C.c_int32),
+        ("real_time_multiplier", C.c_float),
+        ("smoke_enable_decay", C.c_int32),
+        ("smoke_decay_rate", C.c_float),
+        ("obstacle_enable", C.c_int32),
+        ("obstacle_center_x", C.c_int32),
+        ("obstacle_center_y", C.c_int32),
+        ("obstacle_radius", C.c_float),
+        ("density", C.c_float),
+        ("drag_coeff", C.c_float),
+        ("viscosity", C.c_float),
+        ("block_size_x", C.c_int32),
+        ("block_size_y", C.c_int32),
+    ]
+
+    def copy(self) -> "SayalConfig":
+        out = SayalConfig()
+        C.memmove(C.byref(out), C.byref(self), C.sizeof(SayalConfig))
+        return out
+
+    def as_dict(self) -> dict:
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+class SayalSource(C.Structure):
+    _fields_ = [
+        ("active", C.c_int32),
+        ("smoke", C.c_float),
+        ("velocity", C.c_float),
+        ("x", C.c_int32),
+        ("y", C.c_int32),
+    ]
+
+
+class SayalSlab(C.Structure):
+    _fields_ = [
+        ("global_height", C.c_int32),
+        ("row0", C.c_int32),
+        ("rows", C.c_int32),
+        ("halo", C.c_int32),
+    ]
+
+
+# every symbol include/sayal.h declares: (name, restype, argtypes)
+_cfgp = C.POINTER(SayalConfig)
+_srcp = C.POINTER(SayalSource)
+_simp = C.c_void_p
+SYMBOLS = [
+    ("sayal_config_defaults", C.c_int, [C.c_int32, C.c_int32, _cfgp]),
+    ("sayal_config_load", C.c_int, [C.c_char_p, _cfgp]),
+    ("sayal_config_parse", C.c_int, [C.c_char_p, C.c_size_t, _cfgp]),
+    ("sayal_create", C.c_int, [_cfgp, C.c_int32, C.POINTER(_simp)]),
+    ("sayal_create_slab", C.c_int, [_cfgp, C.c_int32, C.POINTER(SayalSlab), C.POINTER(_simp)]),
+    ("sayal_destroy", None, [_simp]),
+    ("sayal_step", C.c_int, [_simp, _srcp, C.c_float]),
+    ("sayal_run", C.c_int, [_simp, C.c_int32, C.c_float]),
+    ("sayal_sync", C.c_int, [_simp]),
+    ("sayal_get_field", C.c_int, [_simp, C.c_int32, C.c_void_p]),
+    ("sayal_set_field", C.c_int, [_simp, C.c_int32, C.c_void_p]),
+    ("sayal_device_ptr", C.c_int, [_simp, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    ("sayal_pressure_range", C.c_int, [_simp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    ("sayal_sample_velocity", C.c_int, [_simp, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("sayal_stage_forces", C.c_int, [_simp, _srcp, C.c_float]),
+    ("sayal_stage_zero_pressure", C.c_int, [_simp]),
+    ("sayal_stage_projection", C.c_int, [_simp, C.c_int32, C.c_float]),
+    ("sayal_stage_extrapolation", C.c_int, [_simp]),
+    ("sayal_stage_advect_velocity", C.c_int, [_simp, C.c_float]),
+    ("sayal_stage_advect_smoke", C.c_int, [_simp, C.c_float]),
+    ("sayal_set_option", C.c_int, [_simp, C.c_char_p, C.c_int64]),
+    ("sayal_get_option", C.c_int, [_simp, C.c_char_p, C.POINTER(C.c_int64)]),
+    ("sayal_launch_count", C.c_int64, [_simp]),
+    ("sayal_stream", C.c_void_p, [_simp]),
+    ("sayal_slab_pack_edge", C.c_int, [_simp, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    ("sayal_slab_unpack_ghost", C.c_int, [_simp, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    ("sayal_last_error", C.c_char_p, []),
+    ("sayal_abi_version", C.c_int, []),
+]
+
+_lib = None
+
+
+class SayalError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"sayal error {code}: {message}")
+        self.code = code
+
+
+def load() -> C.CDLL:
+    """Load libsayal_b200.so (built by opensayal_b200/csrc/Makefile or __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("SAYAL_B200_LIB", LIB_PATH))
+    if not path.exists():
+        raise ImportError(
+            f"{path} not found: the CUDA extension is the product and has no fallback. "
+            "Build it with `make -C opensayal_b200/csrc` or `python -c 'import __graft_entry__ as g; g.build()'`.")
+    lib = C.CDLL(str(path))
+    for name, restype, argtypes in SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError here = header and library disagree
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.sayal_abi_version() != 1:
+        raise ImportError("libsayal_b200.so: ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(code: int) -> None:
+    if code != SAYAL_OK:
+        msg = load().sayal_last_error()
+        raise SayalError(code, msg.decode() if msg else "")

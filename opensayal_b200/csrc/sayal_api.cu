@@ -1,0 +1,504 @@
+// sayal_api.cu — the C ABI of include/sayal.h over the CUDA step path.  Host-side mirror of
+// Fluid::Fluid / ~Fluid / update (/root/reference/src/fluid.cu:41-97, 770-795).
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "sayal_internal.h"
+
+namespace sayal {
+
+static thread_local std::string g_last_error;
+
+int set_error(int code, const char* msg) {
+  g_last_error = msg ? msg : "";
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      char m__[320];                                                                     \
+      snprintf(m__, sizeof m__, "%s failed: %s", #expr, cudaGetErrorString(e__));        \
+      return set_error(SAYAL_ECUDA, m__);                                                \
+    }                                                                                    \
+  } while (0)
+
+#define TRY(expr)            \
+  do {                       \
+    int r__ = (expr);        \
+    if (r__ != SAYAL_OK) return r__; \
+  } while (0)
+
+static size_t field_elems(const Sim* s) { return (size_t)s->g.pitch * s->g.local_rows; }
+
+static void free_sim(Sim* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  for (int k = 0; k < 4; k++)
+    if (s->graph[k]) cudaGraphExecDestroy(s->graph[k]);
+  float* f[] = {s->u, s->v, s->p, s->smoke, s->u_buf, s->v_buf, s->smoke_buf};
+  for (float* q : f)
+    if (q) cudaFree(q);
+  if (s->flags) cudaFree(s->flags);
+  if (s->d_is_solid) cudaFree(s->d_is_solid);
+  if (s->d_total_s) cudaFree(s->d_total_s);
+  if (s->d_range) cudaFree(s->d_range);
+  if (s->d_overflow) cudaFree(s->d_overflow);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+static void invalidate_graphs(Sim* s) {
+  for (int k = 0; k < 4; k++)
+    if (s->graph[k]) {
+      cudaGraphExecDestroy(s->graph[k]);
+      s->graph[k] = nullptr;
+    }
+}
+
+static int create_impl(const sayal_config* c, int device, const sayal_slab* slab, Sim** out) {
+  if (!c || !out) return set_error(SAYAL_EINVAL, "sayal_create: null argument");
+  if (c->width < 4 || c->height < 4) return set_error(SAYAL_EINVAL, "sayal_create: width and height must be >= 4");
+  if ((int64_t)c->width * c->height >= (int64_t)1 << 31)
+    return set_error(SAYAL_EINVAL, "sayal_create: width*height must fit int32 (reference limit, fluid.cu:163)");
+  if ((int)c->cell_size < 1) return set_error(SAYAL_EINVAL, "sayal_create: cell_size must be an integer >= 1 (fluid.cuh:46)");
+  if (c->proj_n < 0) return set_error(SAYAL_EINVAL, "sayal_create: projection.n must be >= 0");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return set_error(SAYAL_EINVAL, "sayal_create: no such CUDA device");
+  CUDA_TRY(cudaSetDevice(device));
+
+  Sim* s = new (std::nothrow) Sim();
+  if (!s) return set_error(SAYAL_ENOMEM, "sayal_create: out of host memory");
+  std::memset(s, 0, sizeof(Sim));
+  s->cfg = *c;
+  s->device = device;
+  Grid& g = s->g;
+  g.W = c->width;
+  g.H = c->height;
+  g.pitch = (c->width + 3) & ~3;
+  g.h = (int)c->cell_size;
+  if (slab && slab->rows > 0) {
+    if (slab->global_height != c->height || slab->row0 < 0 || slab->row0 + slab->rows > c->height || slab->halo < 0) {
+      delete s;
+      return set_error(SAYAL_EINVAL, "sayal_create_slab: slab does not fit the domain");
+    }
+    int lo = slab->row0 - slab->halo, hi = slab->row0 + slab->rows + slab->halo;
+    if (lo < 0) lo = 0;
+    if (hi > c->height) hi = c->height;
+    g.row_base = lo;
+    g.local_rows = hi - lo;
+    g.own_lo = slab->row0 - lo;
+    g.own_hi = g.own_lo + slab->rows;
+  } else {
+    g.row_base = 0;
+    g.local_rows = c->height;
+    g.own_lo = 0;
+    g.own_hi = c->height;
+  }
+  Phys& p = s->ph;
+  p.o = c->proj_o;
+  p.density = c->density;
+  p.g = c->g;
+  p.drag_coeff = c->drag_coeff;
+  p.wt_speed = c->wt_speed;
+  p.wt_smoke = c->wt_smoke;
+  p.wt_height = c->wt_pipe_height;
+  p.wt_smoke_length = c->wt_smoke_length;
+  p.wt_smoke_count = c->wt_smoke_count;
+  p.wt_smoke_height = c->wt_smoke_height;
+  p.enable_pressure = c->enable_pressure != 0;
+  p.enable_smoke = c->enable_smoke != 0;
+  p.enable_decay = c->smoke_enable_decay != 0;
+  p.decay_rate = c->smoke_decay_rate;
+  p.enable_drain = c->enable_drain != 0;
+  p.obstacle_enable = c->obstacle_enable != 0;
+  p.obstacle_cx = c->obstacle_center_x;
+  p.obstacle_cy = c->obstacle_center_y;
+  p.wt_pipe_length = c->wt_pipe_length;
+  p.wt_pipe_height = c->wt_pipe_height;
+  p.obstacle_radius = c->obstacle_radius;
+
+  s->projection_kernel = 1;
+  s->temporal_block = 0;  // 0 = auto
+  s->use_graph = 1;
+
+  auto fail = [&](int code) {
+    free_sim(s);
+    return code;
+  };
+  cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) return fail(set_error(SAYAL_ECUDA, cudaGetErrorString(e)));
+  size_t bytes = field_elems(s) * sizeof(float);
+  float** fields[] = {&s->u, &s->v, &s->p, &s->smoke, &s->u_buf, &s->v_buf, &s->smoke_buf};
+  for (float** f : fields) {
+    e = cudaMalloc(f, bytes);
+    if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
+    cudaMemsetAsync(*f, 0, bytes, s->stream);
+  }
+  e = cudaMalloc(&s->flags, field_elems(s));
+  if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
+  e = cudaMalloc(&s->d_range, 2 * sizeof(int32_t));
+  if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
+  e = cudaMalloc(&s->d_overflow, sizeof(int32_t));
+  if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
+  cudaMemsetAsync(s->d_overflow, 0, sizeof(int32_t), s->stream);
+  int r = launch_build_flags(s);
+  if (r != SAYAL_OK) return fail(r);
+  e = cudaStreamSynchronize(s->stream);
+  if (e != cudaSuccess) return fail(set_error(SAYAL_ECUDA, cudaGetErrorString(e)));
+  *out = s;
+  return SAYAL_OK;
+}
+
+static void swap_ptr(float*& a, float*& b) {
+  float* t = a;
+  a = b;
+  b = t;
+}
+
+static int projection(Sim* s, int iterations, float d_t) {
+  if (iterations <= 0) return SAYAL_OK;
+  if (s->projection_kernel == 1) return launch_projection_tiled(s, iterations, d_t);
+  return launch_projection_plain(s, iterations, d_t);
+}
+
+static int advect_velocity(Sim* s, float d_t) {
+  TRY(launch_advect(s, d_t, true, false));
+  swap_ptr(s->u, s->u_buf);  // update_velocity_advection_at (fluid.cu:614-617) as a pointer swap
+  swap_ptr(s->v, s->v_buf);
+  s->parity ^= 1;
+  return SAYAL_OK;
+}
+
+static int advect_smoke(Sim* s, float d_t) {
+  TRY(launch_advect(s, d_t, false, true));
+  swap_ptr(s->smoke, s->smoke_buf);  // update_smoke_advection_at (fluid.cu:569-571)
+  s->parity ^= 2;
+  return SAYAL_OK;
+}
+
+// Fluid::update (fluid.cu:770-795)
+static int step_impl(Sim* s, const sayal_source* src, float d_t) {
+  TRY(launch_forces(s, src, d_t));
+  if (s->ph.enable_pressure) TRY(launch_zero_pressure(s));
+  // viscosity: the reference's racy diffusion loop (fluid.cu:185-190, H1) is out of scope; see DESIGN.md
+  TRY(projection(s, s->cfg.proj_n, d_t));
+  if (s->ph.enable_pressure) {
+    TRY(launch_pressure_range(s));
+    s->range_valid = false;
+  }
+  TRY(launch_extrapolation(s));
+  TRY(advect_velocity(s, d_t));
+  if (s->ph.enable_smoke && s->ph.wt_smoke != 0.f) TRY(advect_smoke(s, d_t));  // decay fused (fluid.cu:792)
+  return SAYAL_OK;
+}
+
+static bool is_slab(const Sim* s) { return s->g.local_rows != s->g.H; }
+
+}  // namespace sayal
+
+using namespace sayal;
+
+struct sayal_sim {
+  Sim impl;
+};
+static inline Sim* S(sayal_sim* p) { return reinterpret_cast<Sim*>(p); }
+
+extern "C" {
+
+int sayal_abi_version(void) { return SAYAL_ABI_VERSION; }
+const char* sayal_last_error(void) { return g_last_error.c_str(); }
+
+int sayal_create(const sayal_config* cfg, int32_t device, sayal_sim** out) {
+  Sim* s = nullptr;
+  int r = create_impl(cfg, device, nullptr, &s);
+  if (r == SAYAL_OK) *out = reinterpret_cast<sayal_sim*>(s);
+  return r;
+}
+
+int sayal_create_slab(const sayal_config* cfg, int32_t device, const sayal_slab* slab, sayal_sim** out) {
+  Sim* s = nullptr;
+  int r = create_impl(cfg, device, slab, &s);
+  if (r == SAYAL_OK) *out = reinterpret_cast<sayal_sim*>(s);
+  return r;
+}
+
+void sayal_destroy(sayal_sim* sim) { free_sim(S(sim)); }
+
+int sayal_step(sayal_sim* sim, const sayal_source* src, float d_t) {
+  if (!sim) return set_error(SAYAL_EINVAL, "sayal_step: null sim");
+  Sim* s = S(sim);
+  if (is_slab(s)) return set_error(SAYAL_EINVAL, "sayal_step: slab sims are stepped stage by stage with ghost exchange (see opensayal_b200/slab.py)");
+  CUDA_TRY(cudaSetDevice(s->device));
+  return step_impl(s, src, d_t);
+}
+
+int sayal_run(sayal_sim* sim, int32_t steps, float d_t) {
+  if (!sim) return set_error(SAYAL_EINVAL, "sayal_run: null sim");
+  Sim* s = S(sim);
+  if (is_slab(s)) return set_error(SAYAL_EINVAL, "sayal_run: slab sims are stepped stage by stage with ghost exchange");
+  if (steps < 0) return set_error(SAYAL_EINVAL, "sayal_run: steps < 0");
+  CUDA_TRY(cudaSetDevice(s->device));
+  if (s->graph_dt != d_t) {
+    invalidate_graphs(s);
+    s->graph_dt = d_t;
+  }
+  int remaining = steps;
+  // One graph per starting parity holds ONE step; replaying it is followed by the same pointer swaps on
+  // the host that capture performed, so the next replay (or eager call) sees the right front buffers.
+  while (s->use_graph && remaining > 0) {
+    int slot = s->parity & 3;
+    if (!s->graph[slot]) {
+      cudaGraph_t graph = nullptr;
+      int64_t before = s->launches;
+      CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+      int r = step_impl(s, nullptr, d_t);
+      cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+      s->graph_launches[slot] = s->launches - before;
+      s->launches = before;  // capturing launches nothing
+      if (r != SAYAL_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return r;
+      }
+      if (e != cudaSuccess) return set_error(SAYAL_ECUDA, cudaGetErrorString(e));
+      e = cudaGraphInstantiate(&s->graph[slot], graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) return set_error(SAYAL_ECUDA, cudaGetErrorString(e));
+      s->graph_post[slot] = {s->u, s->v, s->u_buf, s->v_buf, s->smoke, s->smoke_buf, s->parity};
+    }
+    CUDA_TRY(cudaGraphLaunch(s->graph[slot], s->stream));
+    const Sim::PtrState& ps = s->graph_post[slot];
+    s->u = ps.u; s->v = ps.v; s->u_buf = ps.u_buf; s->v_buf = ps.v_buf;
+    s->smoke = ps.smoke; s->smoke_buf = ps.smoke_buf; s->parity = ps.parity;
+    s->launches += s->graph_launches[slot];
+    if (s->ph.enable_pressure) s->range_valid = false;
+    remaining--;
+  }
+  for (; remaining > 0; remaining--) TRY(step_impl(s, nullptr, d_t));
+  return SAYAL_OK;
+}
+
+int sayal_sync(sayal_sim* sim) {
+  if (!sim) return set_error(SAYAL_EINVAL, "sayal_sync: null sim");
+  CUDA_TRY(cudaStreamSynchronize(S(sim)->stream));
+  return SAYAL_OK;
+}
+
+
+static int field_info(Sim* s, int field, void** ptr, size_t* elem, bool* dense) {
+  *elem = 4;
+  *dense = false;
+  switch (field) {
+    case SAYAL_U: *ptr = s->u; return SAYAL_OK;
+    case SAYAL_V: *ptr = s->v; return SAYAL_OK;
+    case SAYAL_P: *ptr = s->p; return SAYAL_OK;
+    case SAYAL_SMOKE: *ptr = s->smoke; return SAYAL_OK;
+    case SAYAL_IS_SOLID:
+    case SAYAL_TOTAL_S: {
+      if (!s->d_is_solid) {  // built on demand: the step path itself only needs the 1-byte flags
+        size_t n = (size_t)s->g.W * s->g.local_rows * sizeof(int32_t);
+        CUDA_TRY(cudaMalloc(&s->d_is_solid, n));
+        CUDA_TRY(cudaMalloc(&s->d_total_s, n));
+        TRY(launch_export_masks(s));
+      }
+      *ptr = field == SAYAL_IS_SOLID ? s->d_is_solid : s->d_total_s;
+      *dense = true;
+      return SAYAL_OK;
+    }
+  }
+  return set_error(SAYAL_EINVAL, "unknown field id");
+}
+
+int sayal_get_field(sayal_sim* sim, int32_t field, void* host_dst) {
+  if (!sim || !host_dst) return set_error(SAYAL_EINVAL, "sayal_get_field: null argument");
+  Sim* s = S(sim);
+  CUDA_TRY(cudaSetDevice(s->device));
+  void* p;
+  size_t elem;
+  bool dense;
+  TRY(field_info(s, field, &p, &elem, &dense));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  size_t src_pitch = (dense ? s->g.W : s->g.pitch) * elem;
+  const char* src = (const char*)p + (size_t)s->g.own_lo * src_pitch;
+  CUDA_TRY(cudaMemcpy2D(host_dst, s->g.W * elem, src, src_pitch, s->g.W * elem, s->g.own_hi - s->g.own_lo,
+                        cudaMemcpyDeviceToHost));
+  return SAYAL_OK;
+}
+
+int sayal_set_field(sayal_sim* sim, int32_t field, const void* host_src) {
+  if (!sim || !host_src) return set_error(SAYAL_EINVAL, "sayal_set_field: null argument");
+  Sim* s = S(sim);
+  if (field < SAYAL_U || field > SAYAL_SMOKE) return set_error(SAYAL_EINVAL, "sayal_set_field: only U, V, P, SMOKE are writable (masks derive from the config)");
+  CUDA_TRY(cudaSetDevice(s->device));
+  void* p;
+  size_t elem;
+  bool dense;
+  TRY(field_info(s, field, &p, &elem, &dense));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  char* dst = (char*)p + (size_t)s->g.own_lo * s->g.pitch * elem;
+  CUDA_TRY(cudaMemcpy2D(dst, s->g.pitch * elem, host_src, s->g.W * elem, s->g.W * elem, s->g.own_hi - s->g.own_lo,
+                        cudaMemcpyHostToDevice));
+  return SAYAL_OK;
+}
+
+int sayal_device_ptr(sayal_sim* sim, int32_t field, void** dev_ptr, int64_t* pitch_elems, int32_t* first_row,
+                     int32_t* n_rows) {
+  if (!sim || !dev_ptr) return set_error(SAYAL_EINVAL, "sayal_device_ptr: null argument");
+  Sim* s = S(sim);
+  CUDA_TRY(cudaSetDevice(s->device));
+  void* p;
+  size_t elem;
+  bool dense;
+  TRY(field_info(s, field, &p, &elem, &dense));
+  *dev_ptr = p;
+  if (pitch_elems) *pitch_elems = dense ? s->g.W : s->g.pitch;
+  if (first_row) *first_row = s->g.row_base;
+  if (n_rows) *n_rows = s->g.local_rows;
+  return SAYAL_OK;
+}
+
+static float from_ordered(int32_t e) {
+  int32_t b = e ^ ((e >> 31) & 0x7fffffff);
+  float f;
+  std::memcpy(&f, &b, 4);
+  return f;
+}
+
+int sayal_pressure_range(sayal_sim* sim, float* min_p, float* max_p) {
+  if (!sim) return set_error(SAYAL_EINVAL, "sayal_pressure_range: null sim");
+  Sim* s = S(sim);
+  CUDA_TRY(cudaSetDevice(s->device));
+  if (!s->range_valid) {
+    int32_t r[2];
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaMemcpy(r, s->d_range, sizeof r, cudaMemcpyDeviceToHost));
+    s->min_p = from_ordered(r[0]);
+    s->max_p = from_ordered(r[1]);
+    s->range_valid = true;
+  }
+  if (min_p) *min_p = s->min_p;
+  if (max_p) *max_p = s->max_p;
+  return SAYAL_OK;
+}
+
+int sayal_sample_velocity(sayal_sim* sim, int32_t n, const float* xs, const float* ys, float* out_u, float* out_v) {
+  if (!sim || n < 0 || (n > 0 && (!xs || !ys || !out_u || !out_v)))
+    return set_error(SAYAL_EINVAL, "sayal_sample_velocity: bad argument");
+  if (n == 0) return SAYAL_OK;
+  Sim* s = S(sim);
+  CUDA_TRY(cudaSetDevice(s->device));
+  float* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(float) * 4 * (size_t)n));
+  cudaMemcpyAsync(d, xs, sizeof(float) * n, cudaMemcpyHostToDevice, s->stream);
+  cudaMemcpyAsync(d + n, ys, sizeof(float) * n, cudaMemcpyHostToDevice, s->stream);
+  int r = launch_sample_velocity(s, n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n);
+  if (r == SAYAL_OK) {
+    cudaMemcpyAsync(out_u, d + 2 * (size_t)n, sizeof(float) * n, cudaMemcpyDeviceToHost, s->stream);
+    cudaMemcpyAsync(out_v, d + 3 * (size_t)n, sizeof(float) * n, cudaMemcpyDeviceToHost, s->stream);
+  }
+  cudaError_t e = cudaStreamSynchronize(s->stream);
+  cudaFree(d);
+  if (r != SAYAL_OK) return r;
+  if (e != cudaSuccess) return set_error(SAYAL_ECUDA, cudaGetErrorString(e));
+  return SAYAL_OK;
+}
+
+// ---- stages ---------------------------------------------------------------------------------------
+#define STAGE_PROLOGUE(name)                                          \
+  if (!sim) return set_error(SAYAL_EINVAL, name ": null sim");        \
+  Sim* s = S(sim);                                                    \
+  CUDA_TRY(cudaSetDevice(s->device));
+
+int sayal_stage_forces(sayal_sim* sim, const sayal_source* src, float d_t) {
+  STAGE_PROLOGUE("sayal_stage_forces");
+  return launch_forces(s, src, d_t);
+}
+int sayal_stage_zero_pressure(sayal_sim* sim) {
+  STAGE_PROLOGUE("sayal_stage_zero_pressure");
+  return launch_zero_pressure(s);
+}
+int sayal_stage_projection(sayal_sim* sim, int32_t iterations, float d_t) {
+  STAGE_PROLOGUE("sayal_stage_projection");
+  TRY(projection(s, iterations, d_t));
+  if (s->ph.enable_pressure) {
+    TRY(launch_pressure_range(s));
+    s->range_valid = false;
+  }
+  return SAYAL_OK;
+}
+int sayal_stage_extrapolation(sayal_sim* sim) {
+  STAGE_PROLOGUE("sayal_stage_extrapolation");
+  return launch_extrapolation(s);
+}
+int sayal_stage_advect_velocity(sayal_sim* sim, float d_t) {
+  STAGE_PROLOGUE("sayal_stage_advect_velocity");
+  return advect_velocity(s, d_t);
+}
+int sayal_stage_advect_smoke(sayal_sim* sim, float d_t) {
+  STAGE_PROLOGUE("sayal_stage_advect_smoke");
+  return advect_smoke(s, d_t);
+}
+
+// ---- options --------------------------------------------------------------------------------------
+int sayal_set_option(sayal_sim* sim, const char* key, int64_t value) {
+  if (!sim || !key) return set_error(SAYAL_EINVAL, "sayal_set_option: null argument");
+  Sim* s = S(sim);
+  invalidate_graphs(s);
+  if (!strcmp(key, "projection_kernel")) {
+    if (value != 0 && value != 1) return set_error(SAYAL_EINVAL, "projection_kernel must be 0 or 1");
+    s->projection_kernel = (int)value;
+  } else if (!strcmp(key, "temporal_block")) {
+    if (value < 0 || value > tiled_max_temporal_block()) return set_error(SAYAL_EINVAL, "temporal_block out of range");
+    s->temporal_block = (int)value;
+  } else if (!strcmp(key, "use_graph")) {
+    s->use_graph = value != 0;
+  } else {
+    return set_error(SAYAL_EINVAL, "sayal_set_option: unknown key");
+  }
+  return SAYAL_OK;
+}
+
+int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value) {
+  if (!sim || !key || !value) return set_error(SAYAL_EINVAL, "sayal_get_option: null argument");
+  Sim* s = S(sim);
+  if (!strcmp(key, "projection_kernel")) *value = s->projection_kernel;
+  else if (!strcmp(key, "temporal_block")) *value = s->temporal_block;
+  else if (!strcmp(key, "use_graph")) *value = s->use_graph;
+  else if (!strcmp(key, "halo_overflow")) {
+    int32_t v = 0;
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaMemcpy(&v, s->d_overflow, sizeof v, cudaMemcpyDeviceToHost));
+    *value = v;
+  } else if (!strcmp(key, "pitch")) *value = s->g.pitch;
+  else if (!strcmp(key, "local_rows")) *value = s->g.local_rows;
+  else if (!strcmp(key, "own_lo")) *value = s->g.own_lo;
+  else if (!strcmp(key, "own_hi")) *value = s->g.own_hi;
+  else return set_error(SAYAL_EINVAL, "sayal_get_option: unknown key");
+  return SAYAL_OK;
+}
+
+int64_t sayal_launch_count(sayal_sim* sim) { return sim ? S(sim)->launches : 0; }
+void* sayal_stream(sayal_sim* sim) { return sim ? (void*)S(sim)->stream : nullptr; }
+
+// ---- slab edge rows ---------------------------------------------------------------------------------
+// side 0 = low memory rows (towards r = 0), side 1 = high memory rows.
+int sayal_slab_pack_edge(sayal_sim* sim, int32_t side, int32_t nrows, int32_t field_mask, void* dev_buf) {
+  STAGE_PROLOGUE("sayal_slab_pack_edge");
+  if (!dev_buf) return set_error(SAYAL_EINVAL, "sayal_slab_pack_edge: null buffer");
+  int row0 = side == 0 ? s->g.own_lo : s->g.own_hi - nrows;  // the owned rows next to that side
+  return launch_pack_rows(s, row0, nrows, field_mask, (float*)dev_buf, false);
+}
+
+int sayal_slab_unpack_ghost(sayal_sim* sim, int32_t side, int32_t nrows, int32_t field_mask, const void* dev_buf) {
+  STAGE_PROLOGUE("sayal_slab_unpack_ghost");
+  if (!dev_buf) return set_error(SAYAL_EINVAL, "sayal_slab_unpack_ghost: null buffer");
+  int row0 = side == 0 ? s->g.own_lo - nrows : s->g.own_hi;  // the ghost rows beyond that side
+  return launch_pack_rows(s, row0, nrows, field_mask, (float*)const_cast<void*>(dev_buf), true);
+}
+
+}  // extern "C"

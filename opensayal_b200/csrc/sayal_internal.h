@@ -1,0 +1,102 @@
+// sayal_internal.h — shared declarations of the B200-native step path (not part of the public ABI).
+#ifndef SAYAL_INTERNAL_H
+#define SAYAL_INTERNAL_H
+
+#include <cstdint>
+#include <cstddef>
+
+#include "sayal.h"
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#else
+typedef struct CUstream_st* cudaStream_t;
+typedef struct CUgraphExec_st* cudaGraphExec_t;
+typedef struct CUevent_st* cudaEvent_t;
+#endif
+
+namespace sayal {
+
+// thread-local last-error slot behind sayal_last_error(); returns `code`
+int set_error(int code, const char* msg);
+
+// Cell-flag byte (1 B/cell instead of the reference's two int32 arrays, fluid.cuh:71-72).
+//   bit 0..3  the four face updates of apply_projection_at (fluid.cu:247-261) that are enabled for this
+//             cell: L = left neighbour not solid, R, B (j-1), T (j+1); all zero unless the cell is active
+//   bit 4..6  total_s (fluid.cu:127-142) if the cell is active (interior and not solid), else 0
+//   bit 7     is_solid (fluid.cu:113-124)
+// A fully open interior fluid cell is 0x4F.
+enum : uint8_t { FL_L = 1, FL_R = 2, FL_B = 4, FL_T = 8, FL_SOLID = 0x80, FL_OPEN = 0x4F };
+
+// Geometry of the arrays one sim holds.  Memory row r = H-1-j (fluid.cu:163-165); a y-slab holds
+// global rows [row_base, row_base + local_rows), of which [own_lo, own_hi) (local indices) are owned.
+struct Grid {
+  int W, H;        // global cells
+  int pitch;       // elements per row in every array (multiple of 4)
+  int row_base;    // global memory row of local row 0
+  int local_rows;  // rows held (owned + ghost)
+  int own_lo, own_hi;
+  int h;           // Fluid::cell_size, an int (fluid.cuh:46)
+};
+
+// Scalars of Fluid (fluid.cuh:40-59) that kernels need, passed by value (the reference re-loads
+// them from a device copy of the object in every thread).
+struct Phys {
+  float o, density, g, drag_coeff;
+  float wt_speed, wt_smoke;
+  int wt_height, wt_smoke_length, wt_smoke_count, wt_smoke_height;
+  int enable_pressure, enable_smoke, enable_decay;
+  float decay_rate;
+  // mask formula inputs (fluid.cu:113-124)
+  int enable_drain, obstacle_enable, obstacle_cx, obstacle_cy, wt_pipe_length, wt_pipe_height;
+  float obstacle_radius;
+};
+
+struct Sim {
+  sayal_config cfg;
+  Grid g;
+  Phys ph;
+  int device;
+  cudaStream_t stream;
+  // fp32 fields, local_rows x pitch
+  float *u, *v, *p, *smoke, *u_buf, *v_buf, *smoke_buf;
+  uint8_t* flags;
+  int32_t *d_is_solid, *d_total_s;  // built on demand for get_field / device_ptr
+  int32_t* d_range;                 // ordered-int min / max of pressure
+  int32_t* d_overflow;              // count of back-traces that left the local rows (slab runs)
+  float min_p, max_p;
+  bool range_valid;
+  // options
+  int projection_kernel;  // 0 plain half-sweeps, 1 register tile
+  int temporal_block;     // iterations per pass of the tiled kernel
+  int use_graph;
+  int fuse_forces;
+  // CUDA graph cache for sayal_run: one single-step graph per starting buffer parity, with the
+  // pointer assignment the step leaves behind (the step swaps front and back buffers)
+  cudaGraphExec_t graph[4];   // indexed by `parity`
+  int64_t graph_launches[4];  // kernels one replay of graph[k] stands for
+  struct PtrState { float *u, *v, *u_buf, *v_buf, *smoke, *smoke_buf; int parity; } graph_post[4];
+  float graph_dt;
+  int parity;  // bit 0: (u,v) and their back buffers are swapped; bit 1: smoke and its back buffer are
+  int64_t launches;
+};
+
+// ---- kernels_basic.cu ---------------------------------------------------------------------------
+int launch_build_flags(Sim* s);
+int launch_export_masks(Sim* s);
+int launch_forces(Sim* s, const sayal_source* src, float d_t);
+int launch_zero_pressure(Sim* s);
+int launch_projection_plain(Sim* s, int iterations, float d_t);
+int launch_pressure_range(Sim* s);
+int launch_extrapolation(Sim* s);
+int launch_advect(Sim* s, float d_t, bool velocity, bool smoke);
+int launch_sample_velocity(Sim* s, int n, const float* d_xs, const float* d_ys, float* d_ou, float* d_ov);
+int launch_pack_rows(Sim* s, int local_row0, int nrows, int field_mask, float* dev_buf, bool unpack);
+
+// ---- projection_tile.cu --------------------------------------------------------------------------
+int launch_projection_tiled(Sim* s, int iterations, float d_t);
+int tiled_max_temporal_block();
+
+}  // namespace sayal
+
+#endif

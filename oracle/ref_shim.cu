@@ -13,6 +13,7 @@
  */
 #include <cstdint>
 #include <cstring>
+#include <malloc.h>
 #include <new>
 
 #include <cuda_runtime.h>
@@ -82,6 +83,11 @@ extern "C" {
 
 int ref_create(const sayal_config* c, int device, ref_sim** out) {
   if (cudaSetDevice(device) != cudaSuccess) return SAYAL_ECUDA;
+  /* H2: Fluid::init_device_memory malloc()s total_s and only ever ++'s it (fluid.cu:102-103, 127-142), so the
+   * reference is correct only when malloc hands out fresh zero pages.  In a long-lived test process glibc's
+   * dynamic mmap threshold grows and recycles dirty heap memory instead.  Pin the threshold so that every
+   * allocation of the size of a field is a fresh mmap, as it is in the reference's own short-lived process. */
+  mallopt(M_MMAP_THRESHOLD, 16 * 1024);
   ref_sim* s = new (std::nothrow) ref_sim();
   if (!s) return SAYAL_ENOMEM;
   s->W = c->width;

@@ -1,0 +1,264 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar: bit-exact.  Both sides execute the same IEEE-754 operation sequence, so integer flags
+AND fp32 fields must be equal element for element (np.array_equal; -0.0 == +0.0 is accepted).
+"""
+import numpy as np
+import pytest
+
+from opensayal_b200 import Config, Fluid, Source
+from opensayal_b200._abi import SayalSource
+from opensayal_b200.synthetic import baseline_config, synthetic_fields
+from oracle.oracle import OracleSim
+
+pytestmark = pytest.mark.gpu
+
+
+def pair(cfg, seed=1234, amplitude=40.0, fields=("u", "v", "smoke")):
+    W, H = cfg.c.width, cfg.c.height
+    gpu, cpu = Fluid(cfg), OracleSim(cfg.c)
+    u, v, sm = synthetic_fields(W, H, seed=seed, amplitude=amplitude)
+    for name, a in (("u", u), ("v", v), ("smoke", sm)):
+        if name in fields:
+            gpu.set_field(name, a)
+            cpu.set_field(name, a)
+    return gpu, cpu
+
+
+def assert_same(gpu, cpu, names=("u", "v", "smoke"), what=""):
+    for n in names:
+        a, b = gpu.get_field(n), cpu.get_field(n)
+        if not np.array_equal(a, b):
+            bad = np.argwhere(a != b)
+            r, i = bad[0]
+            raise AssertionError(f"{what} {n}: {len(bad)} cells differ, first at row {r} col {i}: "
+                                 f"gpu {a[r, i]!r} oracle {b[r, i]!r}; max |diff| {np.nanmax(np.abs(a - b))}")
+
+
+CONFIGS = {
+    "tank_256x144": lambda: baseline_config(0),
+    "tunnel_384x216": lambda: baseline_config(1, width=384, height=216),
+    "odd_203x157": lambda: Config.defaults(203, 157, **{"fluid.viscosity": 0.0, "sim.wind_tunnel.speed": 60.0,
+                                                          "sim.obstacle.radius": 17.5, "sim.physics.g": -3.0}),
+    "closed_disc_130x170": lambda: Config.defaults(130, 170, **{"fluid.viscosity": 0.0, "sim.enable_drain": 0,
+                                                                 "sim.obstacle.center_x": 40,
+                                                                 "sim.obstacle.center_y": 120,
+                                                                 "sim.obstacle.radius": 23.0}),
+}
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_masks_bit_exact(name):
+    cfg = CONFIGS[name]()
+    gpu, cpu = Fluid(cfg), OracleSim(cfg.c)
+    assert np.array_equal(gpu.is_solid, cpu.get_field("is_solid"))
+    assert np.array_equal(gpu.total_s, cpu.get_field("total_s"))
+
+
+def test_masks_pipe_walls_and_full_size():
+    cfg = baseline_config(1)
+    cfg.c.wt_pipe_length = 300  # dead in the shipped parser (config_parser.cpp:64) but part of the formula
+    gpu, cpu = Fluid(cfg), OracleSim(cfg.c)
+    assert np.array_equal(gpu.is_solid, cpu.get_field("is_solid"))
+    assert np.array_equal(gpu.total_s, cpu.get_field("total_s"))
+    assert gpu.is_solid.sum() > 8967
+
+
+def test_forces_bit_exact():
+    cfg = baseline_config(1, width=384, height=216)
+    cfg["sim.physics.g"] = -5.0
+    cfg["fluid.drag_coeff"] = 0.3
+    cfg["sim.wind_tunnel.smoke_count"] = 3
+    cfg["sim.wind_tunnel.smoke_height"] = 10
+    gpu, cpu = pair(cfg)
+    src = Source(True, 0.7, 1.5, (200, 100))
+    gpu.stage_forces(src, 0.05)
+    cpu.forces(src._c(), 0.05)
+    assert_same(gpu, cpu, what="forces")
+    gpu.stage_forces(None, 0.02)
+    cpu.forces(None, 0.02)
+    assert_same(gpu, cpu, what="forces(inactive)")
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_projection_bit_exact(name, kernel):
+    cfg = CONFIGS[name]()
+    cfg["sim.enable_pressure"] = 0
+    gpu, cpu = pair(cfg)
+    gpu.set_option("projection_kernel", kernel)
+    gpu.stage_projection(7, 0.05)
+    cpu.projection(7, 0.05)
+    assert_same(gpu, cpu, names=("u", "v"), what=f"projection kernel={kernel}")
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 4, 5, 8, 12])
+def test_tiled_projection_any_temporal_block(T):
+    """Tiling / temporal blocking must not change a bit: several tiles in x and y, n not divisible by T."""
+    cfg = baseline_config(1, width=520, height=470)
+    gpu, cpu = pair(cfg)
+    gpu.set_option("projection_kernel", 1)
+    gpu.set_option("temporal_block", T)
+    gpu.stage_projection(13, 0.05)
+    cpu.projection(13, 0.05)
+    assert_same(gpu, cpu, names=("u", "v"), what=f"tiled T={T}")
+
+
+def test_projection_with_pressure_and_range():
+    cfg = baseline_config(0)
+    gpu, cpu = pair(cfg)
+    gpu.stage_zero_pressure()
+    cpu.zero_pressure()
+    gpu.stage_projection(50, 0.05)
+    cpu.projection(50, 0.05)
+    assert_same(gpu, cpu, names=("u", "v", "p"), what="projection+pressure")
+    assert (gpu.min_pressure, gpu.max_pressure) == cpu.pressure_range()
+
+
+def test_extrapolation_bit_exact():
+    cfg = CONFIGS["odd_203x157"]()
+    gpu, cpu = pair(cfg)
+    gpu.stage_extrapolation()
+    cpu.extrapolation()
+    assert_same(gpu, cpu, names=("u", "v"), what="extrapolation")
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_advection_bit_exact(name):
+    cfg = CONFIGS[name]()
+    cfg["sim.smoke.enable_decay"] = 1
+    cfg["sim.smoke.decay_rate"] = 0.3
+    gpu, cpu = pair(cfg)
+    gpu.stage_advect_velocity(0.05)
+    cpu.advect_velocity(0.05)
+    assert_same(gpu, cpu, names=("u", "v"), what="velocity advection")
+    gpu.stage_advect_smoke(0.05)
+    cpu.advect_smoke(0.05)
+    assert_same(gpu, cpu, names=("smoke",), what="smoke advection + decay")
+
+
+def test_advection_fast_flow_far_backtrace():
+    """Wind-tunnel speeds: back-traces of 10+ cells, leaving the domain on the left (fluid.cu:422-424)."""
+    cfg = baseline_config(1, width=384, height=216)
+    gpu, cpu = pair(cfg, amplitude=400.0)
+    gpu.stage_advect_velocity(0.05)
+    cpu.advect_velocity(0.05)
+    gpu.stage_advect_smoke(0.05)
+    cpu.advect_smoke(0.05)
+    assert_same(gpu, cpu, what="fast advection")
+
+
+def test_sample_velocity_bit_exact():
+    cfg = CONFIGS["closed_disc_130x170"]()
+    gpu, cpu = pair(cfg)
+    rng = np.random.default_rng(5)
+    xs = rng.uniform(-5, 135, 4096).astype(np.float32)
+    ys = rng.uniform(-5, 175, 4096).astype(np.float32)
+    xs[:8] = [0, 1, 0.5, 64.5, 129.5, 130, 65, 64.999]
+    ys[:8] = [0, 1, 0.5, 100.5, 0.5, 170, 120, 85.5]
+    gu, gv = gpu.get_general_velocity(xs, ys)
+    cu, cv = cpu.sample_velocity(xs, ys)
+    assert np.array_equal(gu, cu) and np.array_equal(gv, cv)
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_full_steps_bit_exact(name):
+    cfg = CONFIGS[name]()
+    cfg["sim.projection.n"] = 20
+    gpu, cpu = pair(cfg)
+    names = ("u", "v", "smoke") + (("p",) if cfg.c.enable_pressure else ())
+    for step in range(4):
+        gpu.update(None, cfg.c.d_t)
+        cpu.step(None, cfg.c.d_t)
+        assert_same(gpu, cpu, names=names, what=f"step {step}")
+    if cfg.c.enable_pressure:
+        assert (gpu.min_pressure, gpu.max_pressure) == cpu.pressure_range()
+
+
+def test_interactive_source_steps():
+    cfg = baseline_config(0)
+    cfg["sim.projection.n"] = 10
+    gpu, cpu = pair(cfg)
+    for step in range(3):
+        src = Source(True, 1.0, 3.0, (100 + 10 * step, 70))
+        gpu.update(src, 0.04)
+        cpu.step(src._c(), 0.04)
+    assert_same(gpu, cpu, names=("u", "v", "smoke", "p"), what="interactive")
+
+
+@pytest.mark.parametrize("graph", [0, 1])
+def test_run_equals_repeated_update(graph):
+    cfg = baseline_config(1, width=384, height=216)
+    cfg["sim.projection.n"] = 11  # odd number of passes: exercises the buffer-parity bookkeeping
+    a, _ = pair(cfg)
+    b, _ = pair(cfg)
+    a.set_option("use_graph", graph)
+    a.run(7)
+    a.sync()
+    for _ in range(7):
+        b.update(None)
+    for n in ("u", "v", "smoke"):
+        assert np.array_equal(a.get_field(n), b.get_field(n)), n
+    a.run(4)  # cached graph, different starting parity
+    for _ in range(4):
+        b.update(None)
+    assert np.array_equal(a.get_field("u"), b.get_field("u"))
+    assert a.launch_count == b.launch_count
+
+
+def test_zero_start_wind_tunnel_matches_oracle():
+    """The reference's natural all-zero start (fluid.cu:104-109): inlet drives everything."""
+    cfg = baseline_config(1, width=384, height=216)
+    gpu, cpu = Fluid(cfg), OracleSim(cfg.c)
+    for _ in range(5):
+        gpu.update(None)
+        cpu.step(None)
+    assert_same(gpu, cpu, what="zero start")
+    assert gpu.get_field("smoke").max() > 0
+
+
+def test_full_size_1920x1080_one_step_and_properties():
+    """BASELINE config 2 at full size: one step bit-exact vs the oracle (seconds on one core); then
+    size-independent properties: tiled == plain, and projection contracts the divergence."""
+    cfg = baseline_config(1)
+    gpu, cpu = pair(cfg)
+    gpu.update(None)
+    cpu.step(None)
+    assert_same(gpu, cpu, what="1920x1080 step")
+
+
+def test_large_grid_properties_3840x2160():
+    cfg = baseline_config(2)
+    u, v, sm = synthetic_fields(3840, 2160)
+    outs = []
+    for kernel in (0, 1):
+        f = Fluid(cfg)
+        f.set_field("u", u)
+        f.set_field("v", v)
+        f.set_option("projection_kernel", kernel)
+        f.stage_projection(30, 0.05)
+        outs.append((f.get_field("u"), f.get_field("v"), f.is_solid))
+        f.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    uu, vv, solid = outs[1]
+
+    def mean_div(a, b):
+        d = (a[1:-1, 2:] - a[1:-1, 1:-1]) + (b[:-2, 1:-1] - b[1:-1, 1:-1])
+        return float(np.abs(d[:, :-1][solid[1:-1, 1:-2] == 0]).mean())
+
+    assert mean_div(uu, vv) < 0.25 * mean_div(u, v)
+
+
+def test_errors_are_codes_not_exits():
+    from opensayal_b200 import SayalError
+    cfg = Config.defaults(2, 2)
+    with pytest.raises(SayalError):
+        Fluid(cfg)
+    cfg = Config.defaults(64, 64)
+    with pytest.raises(SayalError):
+        Fluid(cfg, device=99)
+    f = Fluid(cfg)
+    with pytest.raises(SayalError):
+        f.set_option("no_such_option", 1)
+    with pytest.raises(ValueError):
+        f.set_field("u", np.zeros((3, 3), np.float32))
