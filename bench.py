@@ -251,7 +251,7 @@ def bench_ours_single(args):
            "d2h_bytes_per_step": field_bytes / args.steps,
            "protocol": "set_field(u,v,smoke) from pinned host + K x sayal_step(host Source) + get_field(u,v,smoke), wall clock"}
 
-    cpu = cpu_baseline_port(cfg, threads=1, target_seconds=12.0)
+    cpu = None if args.skip_cpu_baseline else cpu_baseline_port(cfg, threads=1, target_seconds=12.0)
     line = {
         "metric": "cell-steps/sec (n=50 SOR)", "value": value, "unit": "cell-steps/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -353,6 +353,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only")
     args = ap.parse_args()
     if args.impl == "reference":
         line = bench_reference(args)

@@ -161,8 +161,10 @@ int sayal_stage_extrapolation(sayal_sim* sim);
 int sayal_stage_advect_velocity(sayal_sim* sim, float d_t);
 int sayal_stage_advect_smoke(sayal_sim* sim, float d_t);
 
-/* Tuning / introspection.  Known keys: "projection_kernel" (0 = plain half-sweeps, 1 = register-tile
- * temporally blocked), "temporal_block" (iterations per pass), "use_graph" (0/1).  */
+/* Tuning / introspection.  set: "projection_kernel" (0 = plain half-sweeps, 1 = register-tile temporally
+ * blocked), "temporal_block" (iterations per pass, 0 = choose), "tile_rows_per_warp" (0 = choose, 8/10/12),
+ * "autotune" (time candidate tile plans on first use), "use_graph".  get: the same plus "plan_temporal_block",
+ * "plan_rows_per_warp", "halo_overflow", "pitch", "local_rows", "own_lo", "own_hi".  No option changes results. */
 int sayal_set_option(sayal_sim* sim, const char* key, int64_t value);
 int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value);
 /* Number of kernels this library has launched on behalf of `sim` since creation. */

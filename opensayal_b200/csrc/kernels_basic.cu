@@ -57,8 +57,9 @@ __global__ void build_flags_kernel(Grid g, Phys p, uint8_t* __restrict__ flags) 
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int lr = blockIdx.y * blockDim.y + threadIdx.y;
   if (i >= g.pitch || lr >= g.local_rows) return;
-  uint8_t f = 0;
+  uint8_t f = FL_SOLID;  // pad columns read as solid: the advection taps rely on it
   if (i < g.W) {
+    f = 0;
     int j = g.H - 1 - (g.row_base + lr);
     bool solid = solid_formula(g, p, i, j);
     if (solid) {
@@ -305,9 +306,17 @@ int launch_extrapolation(Sim* s) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Semi-Lagrangian advection (fluid.cu:364-716).  One kernel produces u', v' and smoke' (+decay) into the
-// back buffers; the host swaps pointers instead of running the reference's copy-back kernels
-// (fluid.cu:614-617, 569-571).
+// Semi-Lagrangian advection (fluid.cu:364-716).  Velocity advection writes u', v' and smoke advection
+// (+decay) writes smoke' into the back buffers; the host swaps pointers instead of running the reference's
+// copy-back kernels (fluid.cu:614-617, 569-571).
+//
+// Two things keep the instruction count down without changing a bit of the result:
+//   * HC = 1 specialises cell_size == 1 (every shipped config): x / 1.0f == x, (k + 0.5) * 1 == k + 0.5, so
+//     all divisions by the cell size disappear.  HC = 0 keeps the general integer cell size.
+//   * Once the base cell of a sample is a fluid cell it is an interior cell (walls are always solid), so
+//     its 3x3 neighbourhood is inside the array; the one exception, column W when the drain is open, reads
+//     a pad byte (or column 0 of the next row) that build_flags marks solid.  Taps therefore need no
+//     bounds test, only the solid bit.
 // ---------------------------------------------------------------------------------------------------
 struct View {
   const float* __restrict__ u;
@@ -319,170 +328,242 @@ struct View {
 
 __device__ __forceinline__ int f2i_rz(float x) { return __float2int_rz(x); }  // cvt.rzi.s32.f32: saturating, NaN -> 0
 
-// Fluid::is_valid_fluid (fluid.cu:360-362); lr is returned for the caller's load
-__device__ __forceinline__ bool fluid_at(const Grid& g, const View& w, int i, int j, size_t* k) {
+template <int HC>
+__device__ __forceinline__ float div_h(float x, float hf) { return HC == 1 ? x : __fdiv_rn(x, hf); }
+template <int HC>
+__device__ __forceinline__ float mul_h(int k, int h) { return HC == 1 ? (float)k : (float)(k * h); }
+template <int HC>
+__device__ __forceinline__ float pos_half(int k, int h) {
+  float c = __fadd_rn((float)k, 0.5f);
+  return HC == 1 ? c : __fmul_rn(c, (float)h);
+}
+
+// Fluid::is_valid_fluid (fluid.cu:360-362) with all bounds tests, for the base cell of a sample.  On success
+// *k is the cell's index and its 3x3 neighbourhood is addressable.
+__device__ __forceinline__ bool base_fluid(const Grid& g, const View& w, int i, int j, long* k) {
   if (i < 0 || j < 0 || i >= g.W || j >= g.H) return false;
   int lr = (g.H - 1 - j) - g.row_base;
   if (lr < 0 || lr >= g.local_rows) {  // a slab's back-trace left its ghost rows: report, do not guess
     atomicAdd(w.overflow, 1);
     return false;
   }
-  *k = (size_t)lr * g.pitch + i;
+  long kk = (long)lr * g.pitch + i;
+  if (w.flags[kk] & FL_SOLID) return false;
+  if (lr < 1 || lr > g.local_rows - 2) {  // fluid cell on the first/last local row: only possible in a slab
+    atomicAdd(w.overflow, 1);
+    return false;
+  }
+  *k = kk;
+  return true;
+}
+
+__device__ __forceinline__ bool open_tap(const View& w, long k) { return !(w.flags[k] & FL_SOLID); }
+
+// Fluid::get_general_velocity_y (fluid.cu:418-477).  Memory row of (i, j+1) is k - pitch.
+template <int HC>
+__device__ float general_velocity_y(const Grid& g, const View& w, float x, float y) {
+  const float hf = (float)g.h;
+  const double half = HC == 1 ? 0.5 : (double)g.h / 2.0;
+  int i = f2i_rz(div_h<HC>(x, hf)), j = f2i_rz(div_h<HC>(y, hf));
+  long k;
+  if (!base_fluid(g, w, i, j, &k)) return 0.f;
+  const long up = -(long)g.pitch;
+  float in_x = __fsub_rn(x, mul_h<HC>(i, g.h));
+  float in_y = __fsub_rn(y, mul_h<HC>(j, g.h));
+  float w_y = __fsub_rn(1.0f, div_h<HC>(in_y, hf));
+  float n_y = __fsub_rn(1.0f, w_y);
+  float avg = 0.f;
+  if ((double)in_x < half) {
+    float d_x = (float)__dsub_rn(half, (double)in_x);
+    float w_x = __fsub_rn(1.0f, div_h<HC>(d_x, hf));
+    float n_x = __fsub_rn(1.0f, w_x);
+    avg = __fmaf_rn(__fmul_rn(w_y, w_x), w.v[k], avg);
+    if (open_tap(w, k - 1)) avg = __fmaf_rn(__fmul_rn(w_y, n_x), w.v[k - 1], avg);
+    if (open_tap(w, k - 1 + up)) avg = __fmaf_rn(__fmul_rn(n_y, n_x), w.v[k - 1 + up], avg);
+    if (open_tap(w, k + up)) avg = __fmaf_rn(__fmul_rn(n_y, w_x), w.v[k + up], avg);
+  } else {
+    float d_x = (float)__dsub_rn((double)in_x, half);
+    float w_x = __fsub_rn(1.0f, div_h<HC>(d_x, hf));
+    float n_x = __fsub_rn(1.0f, w_x);
+    avg = __fmaf_rn(__fmul_rn(w_y, w_x), w.v[k], avg);
+    if (open_tap(w, k + up)) avg = __fmaf_rn(__fmul_rn(n_y, w_x), w.v[k + up], avg);
+    if (open_tap(w, k + 1 + up)) avg = __fmaf_rn(__fmul_rn(n_y, n_x), w.v[k + 1 + up], avg);
+    if (open_tap(w, k + 1)) avg = __fmaf_rn(__fmul_rn(w_y, n_x), w.v[k + 1], avg);
+  }
+  return avg;
+}
+
+// Fluid::get_general_velocity_x (fluid.cu:479-539).  Memory row of (i, j-1) is k + pitch.
+template <int HC>
+__device__ float general_velocity_x(const Grid& g, const View& w, float x, float y) {
+  const float hf = (float)g.h;
+  const double half = HC == 1 ? 0.5 : (double)g.h / 2.0;
+  int i = f2i_rz(div_h<HC>(x, hf)), j = f2i_rz(div_h<HC>(y, hf));
+  long k;
+  if (!base_fluid(g, w, i, j, &k)) return 0.f;
+  const long up = -(long)g.pitch, down = (long)g.pitch;
+  float in_x = __fsub_rn(x, mul_h<HC>(i, g.h));
+  float in_y = __fsub_rn(y, mul_h<HC>(j, g.h));
+  float w_x = __fsub_rn(1.0f, div_h<HC>(in_x, hf));
+  float n_x = __fsub_rn(1.0f, w_x);
+  float avg = 0.f;
+  if ((double)in_y <= half) {  // note <= here, < in _y (fluid.cu:493 vs 432)
+    float d_y = (float)__dsub_rn(half, (double)in_y);
+    float w_y = __fsub_rn(1.0f, div_h<HC>(d_y, hf));
+    float n_y = __fsub_rn(1.0f, w_y);
+    avg = __fmaf_rn(__fmul_rn(w_y, w_x), w.u[k], avg);
+    if (open_tap(w, k + 1)) avg = __fmaf_rn(__fmul_rn(w_y, n_x), w.u[k + 1], avg);
+    if (open_tap(w, k + down)) avg = __fmaf_rn(__fmul_rn(n_y, w_x), w.u[k + down], avg);
+    if (open_tap(w, k + 1 + down)) avg = __fmaf_rn(__fmul_rn(n_y, n_x), w.u[k + 1 + down], avg);
+  } else {
+    float d_y = (float)__dsub_rn((double)in_y, half);
+    float w_y = __fsub_rn(1.0f, div_h<HC>(d_y, hf));
+    float n_y = __fsub_rn(1.0f, w_y);
+    avg = __fmaf_rn(__fmul_rn(w_y, w_x), w.u[k], avg);
+    if (open_tap(w, k + up)) avg = __fmaf_rn(__fmul_rn(n_y, w_x), w.u[k + up], avg);
+    if (open_tap(w, k + 1)) avg = __fmaf_rn(__fmul_rn(w_y, n_x), w.u[k + 1], avg);
+    if (open_tap(w, k + 1 + up)) avg = __fmaf_rn(__fmul_rn(n_y, n_x), w.u[k + 1 + up], avg);
+  }
+  return avg;
+}
+
+// Fluid::is_valid_fluid for an arbitrary tap of interpolate_smoke, whose base cell may be anything
+__device__ __forceinline__ bool fluid_at(const Grid& g, const View& w, int i, int j, long* k) {
+  if (i < 0 || j < 0 || i >= g.W || j >= g.H) return false;
+  int lr = (g.H - 1 - j) - g.row_base;
+  if (lr < 0 || lr >= g.local_rows) {
+    atomicAdd(w.overflow, 1);
+    return false;
+  }
+  *k = (long)lr * g.pitch + i;
   return !(w.flags[*k] & FL_SOLID);
 }
 
-__device__ __forceinline__ size_t cell_index(const Grid& g, int i, int j) {
-  return (size_t)((g.H - 1 - j) - g.row_base) * g.pitch + i;
-}
-
-// Fluid::get_general_velocity_y (fluid.cu:418-477)
-__device__ float general_velocity_y(const Grid& g, const View& w, float x, float y) {
-  const float hf = (float)g.h;
-  const double half = (double)g.h / 2.0;
-  int i = f2i_rz(__fdiv_rn(x, hf)), j = f2i_rz(__fdiv_rn(y, hf));
-  size_t k;
-  if (!fluid_at(g, w, i, j, &k)) return 0.f;
-  float in_x = __fsub_rn(x, (float)(i * g.h));
-  float in_y = __fsub_rn(y, (float)(j * g.h));
-  float w_y = __fsub_rn(1.0f, __fdiv_rn(in_y, hf));
-  float avg = 0.f;
-  size_t kk;
-  if ((double)in_x < half) {
-    float d_x = (float)__dsub_rn(half, (double)in_x);
-    float w_x = __fsub_rn(1.0f, __fdiv_rn(d_x, hf));
-    float n_x = __fsub_rn(1.0f, w_x), n_y = __fsub_rn(1.0f, w_y);
-    avg = __fmaf_rn(__fmul_rn(w_y, w_x), w.v[k], avg);
-    if (fluid_at(g, w, i - 1, j, &kk)) avg = __fmaf_rn(__fmul_rn(w_y, n_x), w.v[kk], avg);
-    if (fluid_at(g, w, i - 1, j + 1, &kk)) avg = __fmaf_rn(__fmul_rn(n_y, n_x), w.v[kk], avg);
-    if (fluid_at(g, w, i, j + 1, &kk)) avg = __fmaf_rn(__fmul_rn(n_y, w_x), w.v[kk], avg);
-  } else {
-    float d_x = (float)__dsub_rn((double)in_x, half);
-    float w_x = __fsub_rn(1.0f, __fdiv_rn(d_x, hf));
-    float n_x = __fsub_rn(1.0f, w_x), n_y = __fsub_rn(1.0f, w_y);
-    avg = __fmaf_rn(__fmul_rn(w_y, w_x), w.v[k], avg);
-    if (fluid_at(g, w, i, j + 1, &kk)) avg = __fmaf_rn(__fmul_rn(n_y, w_x), w.v[kk], avg);
-    if (fluid_at(g, w, i + 1, j + 1, &kk)) avg = __fmaf_rn(__fmul_rn(n_y, n_x), w.v[kk], avg);
-    if (fluid_at(g, w, i + 1, j, &kk)) avg = __fmaf_rn(__fmul_rn(w_y, n_x), w.v[kk], avg);
-  }
-  return avg;
-}
-
-// Fluid::get_general_velocity_x (fluid.cu:479-539)
-__device__ float general_velocity_x(const Grid& g, const View& w, float x, float y) {
-  const float hf = (float)g.h;
-  const double half = (double)g.h / 2.0;
-  int i = f2i_rz(__fdiv_rn(x, hf)), j = f2i_rz(__fdiv_rn(y, hf));
-  size_t k;
-  if (!fluid_at(g, w, i, j, &k)) return 0.f;
-  float in_x = __fsub_rn(x, (float)(i * g.h));
-  float in_y = __fsub_rn(y, (float)(j * g.h));
-  float w_x = __fsub_rn(1.0f, __fdiv_rn(in_x, hf));
-  float avg = 0.f;
-  size_t kk;
-  if ((double)in_y <= half) {
-    float d_y = (float)__dsub_rn(half, (double)in_y);
-    float w_y = __fsub_rn(1.0f, __fdiv_rn(d_y, hf));
-    float n_x = __fsub_rn(1.0f, w_x), n_y = __fsub_rn(1.0f, w_y);
-    avg = __fmaf_rn(__fmul_rn(w_y, w_x), w.u[k], avg);
-    if (fluid_at(g, w, i + 1, j, &kk)) avg = __fmaf_rn(__fmul_rn(w_y, n_x), w.u[kk], avg);
-    if (fluid_at(g, w, i, j - 1, &kk)) avg = __fmaf_rn(__fmul_rn(n_y, w_x), w.u[kk], avg);
-    if (fluid_at(g, w, i + 1, j - 1, &kk)) avg = __fmaf_rn(__fmul_rn(n_y, n_x), w.u[kk], avg);
-  } else {
-    float d_y = (float)__dsub_rn((double)in_y, half);
-    float w_y = __fsub_rn(1.0f, __fdiv_rn(d_y, hf));
-    float n_x = __fsub_rn(1.0f, w_x), n_y = __fsub_rn(1.0f, w_y);
-    avg = __fmaf_rn(__fmul_rn(w_y, w_x), w.u[k], avg);
-    if (fluid_at(g, w, i, j + 1, &kk)) avg = __fmaf_rn(__fmul_rn(n_y, w_x), w.u[kk], avg);
-    if (fluid_at(g, w, i + 1, j, &kk)) avg = __fmaf_rn(__fmul_rn(w_y, n_x), w.u[kk], avg);
-    if (fluid_at(g, w, i + 1, j + 1, &kk)) avg = __fmaf_rn(__fmul_rn(n_y, n_x), w.u[kk], avg);
-  }
-  return avg;
-}
-
-__device__ __forceinline__ float pos_half(int k, int h) { return __fmul_rn(__fadd_rn((float)k, 0.5f), (float)h); }
-__device__ __forceinline__ float pos_int(int k, int h) { return (float)(k * h); }
-
 // Fluid::interpolate_smoke (fluid.cu:644-716): inverse-distance weights over the quadrant's four centres
+template <int HC>
 __device__ float interpolate_smoke(const Grid& g, const View& w, float x, float y) {
   const float hf = (float)g.h;
-  const double half = (double)g.h / 2.0;
-  int i = f2i_rz(__fdiv_rn(x, hf)), j = f2i_rz(__fdiv_rn(y, hf));
-  float in_x = __fsub_rn(x, (float)(i * g.h));
-  float in_y = __fsub_rn(y, (float)(j * g.h));
+  const double half = HC == 1 ? 0.5 : (double)g.h / 2.0;
+  int i = f2i_rz(div_h<HC>(x, hf)), j = f2i_rz(div_h<HC>(y, hf));
+  float in_x = __fsub_rn(x, mul_h<HC>(i, g.h));
+  float in_y = __fsub_rn(y, mul_h<HC>(j, g.h));
   int di = ((double)in_x < half) ? -1 : 1;
   int dj = ((double)in_y < half) ? -1 : 1;
+  // distances to the centres of (i,j), (i+di,j), (i,j+dj), (i+di,j+dj)  (helper.cuh:77-81)
+  float dx0 = __fsub_rn(x, pos_half<HC>(i, g.h)), dx1 = __fsub_rn(x, pos_half<HC>(i + di, g.h));
+  float dy0 = __fsub_rn(y, pos_half<HC>(j, g.h)), dy1 = __fsub_rn(y, pos_half<HC>(j + dj, g.h));
+  float yy0 = __fmul_rn(dy0, dy0), yy1 = __fmul_rn(dy1, dy1);
+  float dist[4] = {__fsqrt_rn(__fmaf_rn(dx0, dx0, yy0)), __fsqrt_rn(__fmaf_rn(dx1, dx1, yy0)),
+                   __fsqrt_rn(__fmaf_rn(dx0, dx0, yy1)), __fsqrt_rn(__fmaf_rn(dx1, dx1, yy1))};
   float inv[4];
 #pragma unroll
-  for (int t = 0; t < 4; t++) {
-    int ti = i + ((t & 1) ? di : 0), tj = j + ((t & 2) ? dj : 0);
-    float ddx = __fsub_rn(x, pos_half(ti, g.h)), ddy = __fsub_rn(y, pos_half(tj, g.h));
-    float dist = __fsqrt_rn(__fmaf_rn(ddx, ddx, __fmul_rn(ddy, ddy)));
-    inv[t] = (float)__ddiv_rn(1.0, __dadd_rn((double)dist, 1e-6));
-  }
+  for (int t = 0; t < 4; t++)  // float inv = 1.0 / (distance + 1e-6): FP64 (fluid.cu:690-693); rcp.rn == 1.0/x
+    inv[t] = (float)__drcp_rn(__dadd_rn((double)dist[t], 1e-6));
   float sum_inv = __fadd_rn(__fadd_rn(__fadd_rn(inv[0], inv[1]), inv[2]), inv[3]);
   float avg = 0.f;
+  // the common case: base cell is an interior cell => no bounds tests
+  bool interior = i >= 1 && j >= 1 && i <= g.W - 2 && j <= g.H - 2;
+  int lr = (g.H - 1 - j) - g.row_base;
+  if (interior && lr >= 1 && lr <= g.local_rows - 2) {
+    long k = (long)lr * g.pitch + i;
+    long kj = -(long)dj * g.pitch;  // (i, j+dj)
 #pragma unroll
-  for (int t = 0; t < 4; t++) {
-    int ti = i + ((t & 1) ? di : 0), tj = j + ((t & 2) ? dj : 0);
-    float wt = __fdiv_rn(inv[t], sum_inv);
-    size_t kk;
-    if (fluid_at(g, w, ti, tj, &kk)) avg = __fmaf_rn(wt, w.smoke[kk], avg);
+    for (int t = 0; t < 4; t++) {
+      long kk = k + ((t & 1) ? di : 0) + ((t & 2) ? kj : 0);
+      float wt = __fdiv_rn(inv[t], sum_inv);
+      if (open_tap(w, kk)) avg = __fmaf_rn(wt, w.smoke[kk], avg);
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      int ti = i + ((t & 1) ? di : 0), tj = j + ((t & 2) ? dj : 0);
+      float wt = __fdiv_rn(inv[t], sum_inv);
+      long kk;
+      if (fluid_at(g, w, ti, tj, &kk)) avg = __fmaf_rn(wt, w.smoke[kk], avg);
+    }
   }
   return avg;
 }
 
+// avg / count for count in 1..4 (fluid.cu:386, 413): x * 0.5 and x * 0.25 are the correctly rounded quotients,
+// only count == 3 needs a real division
+__device__ __forceinline__ float div_count(float x, int count) {
+  if (count == 3) return __fdiv_rn(x, 3.0f);
+  return __fmul_rn(x, count == 4 ? 0.25f : (count == 2 ? 0.5f : 1.0f));
+}
+
+template <int HC>
 __global__ void __launch_bounds__(256)
-advect_kernel(Grid g, Phys p, View w, float d_t, int do_velocity, int do_smoke, float* __restrict__ u_out,
-              float* __restrict__ v_out, float* __restrict__ smoke_out) {
+advect_velocity_kernel(Grid g, View w, float d_t, float* __restrict__ u_out, float* __restrict__ v_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int lr = g.own_lo + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= g.W || lr >= g.own_hi) return;
+  int r = g.row_base + lr;
+  int j = g.H - 1 - r;
+  long k = (long)lr * g.pitch + i;
+  const long up = -(long)g.pitch, down = (long)g.pitch;
+  // which neighbours exist at all (index_is_valid, fluid.cu:356-358); rows must also be held locally
+  const bool has_l = i > 0, has_r = i < g.W - 1;
+  const bool has_up = j < g.H - 1 && lr > 0, has_dn = j > 0 && lr < g.local_rows - 1;
+  if ((j < g.H - 1 && lr == 0) || (j > 0 && lr == g.local_rows - 1)) atomicAdd(w.overflow, 1);
+  float uk = w.u[k], vk = w.v[k];
+  // get_vertical_edge_velocity (fluid.cu:364-389)
+  float avg_v = vk;
+  int count = 1;
+  if (has_l && has_up && open_tap(w, k - 1 + up)) { avg_v = __fadd_rn(avg_v, w.v[k - 1 + up]); count++; }
+  if (has_up && open_tap(w, k + up)) { avg_v = __fadd_rn(avg_v, w.v[k + up]); count++; }
+  if (has_l && open_tap(w, k - 1)) { avg_v = __fadd_rn(avg_v, w.v[k - 1]); count++; }
+  avg_v = div_count(avg_v, count);
+  float px = __fmaf_rn(-uk, d_t, mul_h<HC>(i, g.h));
+  float py = __fmaf_rn(-avg_v, d_t, pos_half<HC>(j, g.h));
+  u_out[k] = general_velocity_x<HC>(g, w, px, py);
+  // get_horizontal_edge_velocity (fluid.cu:391-416)
+  float avg_u = uk;
+  count = 1;
+  if (has_r && open_tap(w, k + 1)) { avg_u = __fadd_rn(avg_u, w.u[k + 1]); count++; }
+  if (has_dn && open_tap(w, k + down)) { avg_u = __fadd_rn(avg_u, w.u[k + down]); count++; }
+  if (has_r && has_dn && open_tap(w, k + 1 + down)) { avg_u = __fadd_rn(avg_u, w.u[k + 1 + down]); count++; }
+  avg_u = div_count(avg_u, count);
+  px = __fmaf_rn(-avg_u, d_t, pos_half<HC>(i, g.h));
+  py = __fmaf_rn(-vk, d_t, mul_h<HC>(j, g.h));
+  v_out[k] = general_velocity_y<HC>(g, w, px, py);
+}
+
+template <int HC>
+__global__ void __launch_bounds__(256)
+advect_smoke_kernel(Grid g, View w, float d_t, int enable_decay, float decay_rate, float* __restrict__ smoke_out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int lr = g.own_lo + blockIdx.y * blockDim.y + threadIdx.y;
   if (i >= g.W || lr >= g.own_hi) return;
   int j = g.H - 1 - (g.row_base + lr);
-  size_t k = (size_t)lr * g.pitch + i;
-  size_t kk;
-  if (do_velocity) {
-    // get_vertical_edge_velocity (fluid.cu:364-389)
-    float avg_v = w.v[k];
-    int count = 1;
-    if (fluid_at(g, w, i - 1, j + 1, &kk)) { avg_v = __fadd_rn(avg_v, w.v[kk]); count++; }
-    if (fluid_at(g, w, i, j + 1, &kk)) { avg_v = __fadd_rn(avg_v, w.v[kk]); count++; }
-    if (fluid_at(g, w, i - 1, j, &kk)) { avg_v = __fadd_rn(avg_v, w.v[kk]); count++; }
-    avg_v = __fdiv_rn(avg_v, (float)count);
-    float px = __fmaf_rn(-w.u[k], d_t, pos_int(i, g.h));
-    float py = __fmaf_rn(-avg_v, d_t, pos_half(j, g.h));
-    u_out[k] = general_velocity_x(g, w, px, py);
-    // get_horizontal_edge_velocity (fluid.cu:391-416)
-    float avg_u = w.u[k];
-    count = 1;
-    if (fluid_at(g, w, i + 1, j, &kk)) { avg_u = __fadd_rn(avg_u, w.u[kk]); count++; }
-    if (fluid_at(g, w, i, j - 1, &kk)) { avg_u = __fadd_rn(avg_u, w.u[kk]); count++; }
-    if (fluid_at(g, w, i + 1, j - 1, &kk)) { avg_u = __fadd_rn(avg_u, w.u[kk]); count++; }
-    avg_u = __fdiv_rn(avg_u, (float)count);
-    px = __fmaf_rn(-avg_u, d_t, pos_half(i, g.h));
-    py = __fmaf_rn(-w.v[k], d_t, pos_int(j, g.h));
-    v_out[k] = general_velocity_y(g, w, px, py);
+  long k = (long)lr * g.pitch + i;
+  // apply_smoke_advection_at (fluid.cu:560-567): runs on the velocity field AFTER velocity advection
+  float cx = pos_half<HC>(i, g.h), cy = pos_half<HC>(j, g.h);
+  float vx = general_velocity_x<HC>(g, w, cx, cy), vy = general_velocity_y<HC>(g, w, cx, cy);
+  float sm = interpolate_smoke<HC>(g, w, __fmaf_rn(-vx, d_t, cx), __fmaf_rn(-vy, d_t, cy));
+  if (enable_decay) {  // decay_smoke_at (fluid.cu:758-762)
+    float t = __fmaf_rn(-decay_rate, d_t, sm);
+    sm = (float)fmax((double)t, 0.0);
   }
-  if (do_smoke) {
-    // apply_smoke_advection_at (fluid.cu:560-567).  NOTE the reference advects smoke with the velocity
-    // field *after* velocity advection; the caller passes the right buffers.
-    float cx = pos_half(i, g.h), cy = pos_half(j, g.h);
-    float vx = general_velocity_x(g, w, cx, cy), vy = general_velocity_y(g, w, cx, cy);
-    float sm = interpolate_smoke(g, w, __fmaf_rn(-vx, d_t, cx), __fmaf_rn(-vy, d_t, cy));
-    if (p.enable_decay) {  // decay_smoke_at (fluid.cu:758-762)
-      float t = __fmaf_rn(-p.decay_rate, d_t, sm);
-      sm = (float)fmax((double)t, 0.0);
-    }
-    smoke_out[k] = sm;
-  }
+  smoke_out[k] = sm;
 }
 
 int launch_advect(Sim* s, float d_t, bool velocity, bool smoke) {
   dim3 block(64, 4);
   dim3 grid((s->g.W + block.x - 1) / block.x, (s->g.own_hi - s->g.own_lo + block.y - 1) / block.y);
   View w{s->u, s->v, s->smoke, s->flags, s->d_overflow};
-  advect_kernel<<<grid, block, 0, s->stream>>>(s->g, s->ph, w, d_t, velocity ? 1 : 0, smoke ? 1 : 0, s->u_buf,
-                                               s->v_buf, s->smoke_buf);
-  SAYAL_LAUNCH_CHECK(s, "advect_kernel");
+  if (velocity) {
+    if (s->g.h == 1) advect_velocity_kernel<1><<<grid, block, 0, s->stream>>>(s->g, w, d_t, s->u_buf, s->v_buf);
+    else advect_velocity_kernel<0><<<grid, block, 0, s->stream>>>(s->g, w, d_t, s->u_buf, s->v_buf);
+    SAYAL_LAUNCH_CHECK(s, "advect_velocity_kernel");
+  }
+  if (smoke) {
+    if (s->g.h == 1)
+      advect_smoke_kernel<1><<<grid, block, 0, s->stream>>>(s->g, w, d_t, s->ph.enable_decay, s->ph.decay_rate, s->smoke_buf);
+    else
+      advect_smoke_kernel<0><<<grid, block, 0, s->stream>>>(s->g, w, d_t, s->ph.enable_decay, s->ph.decay_rate, s->smoke_buf);
+    SAYAL_LAUNCH_CHECK(s, "advect_smoke_kernel");
+  }
   return SAYAL_OK;
 }
 
@@ -491,8 +572,8 @@ __global__ void sample_velocity_kernel(Grid g, View w, int n, const float* __res
                                        float* __restrict__ ou, float* __restrict__ ov) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
-  ou[t] = general_velocity_x(g, w, xs[t], ys[t]);
-  ov[t] = general_velocity_y(g, w, xs[t], ys[t]);
+  ou[t] = general_velocity_x<0>(g, w, xs[t], ys[t]);
+  ov[t] = general_velocity_y<0>(g, w, xs[t], ys[t]);
 }
 
 int launch_sample_velocity(Sim* s, int n, const float* d_xs, const float* d_ys, float* d_ou, float* d_ov) {

@@ -180,6 +180,35 @@ __device__ __forceinline__ void half_sweep(float (&u)[RY][4], float (&v)[RY - 1]
   }
 }
 
+// One half-sweep when every row of this warp is fully open for both colours: no flags, no branches, and
+// the compiler is free to interleave the independent rows.  `skip0` is set for the tile's first warp, whose
+// row 0 is the carrier row.  Lane 0 does not zero the correction it receives from "lane -1": a warp can only
+// be all-open away from the left wall (X0 > 0), where column X0 is halo and is never written back.
+template <int RY, int Q0>
+__device__ __forceinline__ void half_sweep_open(float (&u)[RY][4], float (&v)[RY - 1][4], float o, bool skip0,
+                                                float* sv_top, float* sv_bot) {
+  constexpr int QL = Q0 ^ ((RY - 1) & 1);
+  if (!skip0) {
+    float vt[4];
+    float2 t = *reinterpret_cast<float2*>(sv_top + 64 * Q0);
+    vt[Q0] = t.x; vt[Q0 + 2] = t.y; vt[1 - Q0] = 0.f; vt[3 - Q0] = 0.f;
+    row_fast<Q0>(u[0], v[0], vt, o, 1);
+    *reinterpret_cast<float2*>(sv_top + 64 * Q0) = make_float2(vt[Q0], vt[Q0 + 2]);
+  }
+#pragma unroll
+  for (int r = 1; r < RY - 1; r++) {
+    if (((r & 1) ^ Q0) == 0) row_fast<0>(u[r], v[r], v[r - 1], o, 1);
+    else row_fast<1>(u[r], v[r], v[r - 1], o, 1);
+  }
+  {
+    float vb[4];
+    float2 t = *reinterpret_cast<float2*>(sv_bot + 64 * QL);
+    vb[QL] = t.x; vb[QL + 2] = t.y; vb[1 - QL] = 0.f; vb[3 - QL] = 0.f;
+    row_fast<QL>(u[RY - 1], vb, v[RY - 2], o, 1);
+    *reinterpret_cast<float2*>(sv_bot + 64 * QL) = make_float2(vb[QL], vb[QL + 2]);
+  }
+}
+
 template <int RY, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) projection_tile_kernel(TileArgs a) {
   constexpr int TH = RY * NW;
@@ -258,22 +287,43 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_tile_kernel(TileArgs a)
   // (fluid.cu:266, 275).  x is a multiple of 4, so the case of row r in half-sweep c is (j0 - r + c) & 1.
   const int j0 = g.H - 1 - (g.row_base + lr0);
   const int q = j0 & 1;  // case of row 0 in the first (even) half-sweep: 0 -> columns 0,2
-  for (int it = 0; it < a.iters; it++) {
-    // The flags never change, and the compiler knows it: left alone it hoists every per-cell mask and
-    // reciprocal out of this loop and spills them.  Make the flag registers opaque once per iteration.
+  static_assert(RY % 2 == 0, "rows per warp must be even: q must be uniform across the CTA's warps");
+  const unsigned all_rows = (1u << RY) - 1u;
+  const unsigned need = w == 0 ? (all_rows & ~1u) : all_rows;
+  const bool all_open = ((fast_a & fast_b) & need) == need;  // warp-uniform
+  const bool skip0 = w == 0;
+  if (all_open) {
+    for (int it = 0; it < a.iters; it++) {
+      if (q == 0) {
+        half_sweep_open<RY, 0>(u, v, a.o, skip0, sv_top, sv_bot);
+        __syncthreads();
+        half_sweep_open<RY, 1>(u, v, a.o, skip0, sv_top, sv_bot);
+        __syncthreads();
+      } else {
+        half_sweep_open<RY, 1>(u, v, a.o, skip0, sv_top, sv_bot);
+        __syncthreads();
+        half_sweep_open<RY, 0>(u, v, a.o, skip0, sv_top, sv_bot);
+        __syncthreads();
+      }
+    }
+  } else {
+    for (int it = 0; it < a.iters; it++) {
+      // The flags never change, and the compiler knows it: left alone it hoists every per-cell mask and
+      // reciprocal out of this loop and spills them.  Make the flag registers opaque once per iteration.
 #pragma unroll
-    for (int r = 0; r < RY; r++) asm volatile("" : "+r"(fl[r]));
-    asm volatile("" : "+r"(fast_a), "+r"(fast_b));
-    if (q == 0) {
-      half_sweep<RY, 0>(u, v, fl, fast_a, fast_b, a.o, lane, sv_top, sv_bot);
-      __syncthreads();
-      half_sweep<RY, 1>(u, v, fl, fast_a, fast_b, a.o, lane, sv_top, sv_bot);
-      __syncthreads();
-    } else {
-      half_sweep<RY, 1>(u, v, fl, fast_a, fast_b, a.o, lane, sv_top, sv_bot);
-      __syncthreads();
-      half_sweep<RY, 0>(u, v, fl, fast_a, fast_b, a.o, lane, sv_top, sv_bot);
-      __syncthreads();
+      for (int r = 0; r < RY; r++) asm volatile("" : "+r"(fl[r]));
+      asm volatile("" : "+r"(fast_a), "+r"(fast_b));
+      if (q == 0) {
+        half_sweep<RY, 0>(u, v, fl, fast_a, fast_b, a.o, lane, sv_top, sv_bot);
+        __syncthreads();
+        half_sweep<RY, 1>(u, v, fl, fast_a, fast_b, a.o, lane, sv_top, sv_bot);
+        __syncthreads();
+      } else {
+        half_sweep<RY, 1>(u, v, fl, fast_a, fast_b, a.o, lane, sv_top, sv_bot);
+        __syncthreads();
+        half_sweep<RY, 0>(u, v, fl, fast_a, fast_b, a.o, lane, sv_top, sv_bot);
+        __syncthreads();
+      }
     }
   }
 
@@ -303,13 +353,16 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_tile_kernel(TileArgs a)
   }
 }
 
-#ifndef KRY
-#define KRY 10
-#endif
-#ifndef KNW
-#define KNW 16
-#endif
-constexpr int kRY = KRY, kNW = KNW;  // 128 x 160 tile, 512 threads, one CTA per SM
+struct Variant {
+  int ry, nw;
+  void (*kernel)(TileArgs);
+};
+const Variant kVariants[] = {
+    {8, 16, projection_tile_kernel<8, 16>},
+    {10, 16, projection_tile_kernel<10, 16>},
+    {12, 16, projection_tile_kernel<12, 16>},
+};
+constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kMaxT = 16;
 
 int tiles_for(int extent, int tile, int stride) {
@@ -317,21 +370,39 @@ int tiles_for(int extent, int tile, int stride) {
   return (extent - tile + stride - 1) / stride + 1;
 }
 
-}  // namespace
+struct Geometry {
+  int halo_x, halo_y, stride_x, stride_y, tiles_x, tiles_y;
+};
 
-int tiled_max_temporal_block() { return kMaxT; }
+bool geometry(const Grid& g, const Variant& v, int T, Geometry* out) {
+  int th = v.ry * v.nw;
+  out->halo_y = 2 * T;
+  out->halo_x = (2 * T + 3) & ~3;
+  out->stride_x = TW - 2 * out->halo_x;
+  out->stride_y = th - 2 * out->halo_y;
+  if (out->stride_x < TW / 4 || out->stride_y < th / 4) return false;  // keep at least a quarter of the tile useful
+  out->tiles_x = tiles_for(g.pitch, TW, out->stride_x);
+  out->tiles_y = tiles_for(g.local_rows, th, out->stride_y);
+  return true;
+}
 
-int launch_projection_tiled(Sim* s, int iterations, float d_t) {
-  (void)d_t;
-  if (s->ph.enable_pressure) return launch_projection_plain(s, iterations, d_t);  // pressure accumulates per cell: plain path
-  constexpr int TH = kRY * kNW;
-  int T = s->temporal_block > 0 ? s->temporal_block : 5;
-  if (T > iterations) T = iterations;
-  // keep at least a quarter of the tile useful
-  while (T > 1 && (TH - 4 * T < TH / 4 || TW - 2 * ((2 * T + 3) & ~3) < TW / 4)) T--;
+// model of one projection of n iterations, in arbitrary units: passes x waves x (load/store + T sweeps) per row
+double model_cost(const Grid& g, const Variant& v, int T, int n, int sms) {
+  Geometry q;
+  if (!geometry(g, v, T, &q)) return 1e30;
+  int passes = (n + T - 1) / T;
+  long tiles = (long)q.tiles_x * q.tiles_y;
+  long waves = (tiles + sms - 1) / sms;
+  return (double)passes * waves * v.ry * (0.45 + 0.13 * T);
+}
+
+int run_passes(Sim* s, int variant, int T, int iterations) {
+  const Variant& v = kVariants[variant];
   int done = 0;
   while (done < iterations) {
     int it = iterations - done < T ? iterations - done : T;
+    Geometry q;
+    if (!geometry(s->g, v, it, &q)) return set_error(SAYAL_EINVAL, "projection tile: temporal block too large for the tile");
     TileArgs a;
     a.g = s->g;
     a.u_in = s->u;
@@ -341,12 +412,11 @@ int launch_projection_tiled(Sim* s, int iterations, float d_t) {
     a.flags = s->flags;
     a.o = s->ph.o;
     a.iters = it;
-    a.halo_y = 2 * it;
-    a.halo_x = (2 * it + 3) & ~3;
-    a.stride_x = TW - 2 * a.halo_x;
-    a.stride_y = TH - 2 * a.halo_y;
-    dim3 grid(tiles_for(s->g.pitch, TW, a.stride_x), tiles_for(s->g.local_rows, TH, a.stride_y));
-    projection_tile_kernel<kRY, kNW><<<grid, kNW * 32, 0, s->stream>>>(a);
+    a.halo_x = q.halo_x;
+    a.halo_y = q.halo_y;
+    a.stride_x = q.stride_x;
+    a.stride_y = q.stride_y;
+    v.kernel<<<dim3(q.tiles_x, q.tiles_y), v.nw * 32, 0, s->stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
       char m[256];
@@ -354,12 +424,96 @@ int launch_projection_tiled(Sim* s, int iterations, float d_t) {
       return set_error(SAYAL_ECUDA, m);
     }
     s->launches++;
-    float* t = s->u; s->u = s->u_buf; s->u_buf = t;
+    float* t = s->u; s->u = s->u_buf; s->u_buf = t;  // ping-pong: neighbouring tiles still read the old halo
     t = s->v; s->v = s->v_buf; s->v_buf = t;
     s->parity ^= 1;
     done += it;
   }
   return SAYAL_OK;
+}
+
+}  // namespace
+
+int tiled_max_temporal_block() { return kMaxT; }
+
+// Choose (tile variant, temporal block) for `iterations` SOR iterations on this grid: rank all candidates
+// with the wave-quantisation model, then time the best few on the live arrays (state saved and restored;
+// every candidate produces the same bits, so the choice never changes results).
+int tiled_prepare(Sim* s, int iterations) {
+  if (s->ph.enable_pressure || iterations <= 0) return SAYAL_OK;
+  if (s->plan_iterations == iterations && s->plan_variant >= 0) return SAYAL_OK;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+  struct Cand { int variant, T; double cost; float ms; };
+  Cand cands[kNumVariants * kMaxT];
+  int nc = 0;
+  for (int v = 0; v < kNumVariants; v++)
+    for (int T = 1; T <= kMaxT && T <= iterations; T++) {
+      if (s->temporal_block > 0 && T != (s->temporal_block < iterations ? s->temporal_block : iterations)) continue;
+      if (s->force_variant >= 0 && v != s->force_variant) continue;
+      double c = model_cost(s->g, kVariants[v], T, iterations, sms);
+      if (c < 1e29) cands[nc++] = {v, T, c, 0.f};
+    }
+  if (nc == 0) return set_error(SAYAL_EINVAL, "projection tile: no feasible tile plan");
+  for (int a = 0; a < nc; a++)  // selection sort by model cost
+    for (int b = a + 1; b < nc; b++)
+      if (cands[b].cost < cands[a].cost) { Cand t = cands[a]; cands[a] = cands[b]; cands[b] = t; }
+  int best = 0;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s->stream, &cap);
+  int ntime = nc < 6 ? nc : 6;
+  if (s->autotune && cap == cudaStreamCaptureStatusNone && ntime > 1) {
+    size_t bytes = sizeof(float) * (size_t)s->g.pitch * s->g.local_rows;
+    float *su = nullptr, *sv = nullptr;
+    if (cudaMalloc(&su, bytes) == cudaSuccess && cudaMalloc(&sv, bytes) == cudaSuccess) {
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaMemcpyAsync(su, s->u, bytes, cudaMemcpyDeviceToDevice, s->stream);
+      cudaMemcpyAsync(sv, s->v, bytes, cudaMemcpyDeviceToDevice, s->stream);
+      int64_t launches = s->launches;
+      int parity = s->parity;
+      float *u0 = s->u, *v0 = s->v, *ub0 = s->u_buf, *vb0 = s->v_buf;
+      float best_ms = 1e30f;
+      for (int c = 0; c < ntime; c++) {
+        float ms_min = 1e30f;
+        for (int rep = 0; rep < 3; rep++) {  // first repetition warms the instruction cache
+          cudaEventRecord(e0, s->stream);
+          int r = run_passes(s, cands[c].variant, cands[c].T, iterations);
+          cudaEventRecord(e1, s->stream);
+          if (r != SAYAL_OK || cudaEventSynchronize(e1) != cudaSuccess) { ms_min = 1e30f; break; }
+          float ms = 0.f;
+          cudaEventElapsedTime(&ms, e0, e1);
+          if (rep > 0 && ms < ms_min) ms_min = ms;
+        }
+        cands[c].ms = ms_min;
+        if (ms_min < best_ms) { best_ms = ms_min; best = c; }
+      }
+      // restore state and bookkeeping: tuning is invisible
+      s->u = u0; s->v = v0; s->u_buf = ub0; s->v_buf = vb0;
+      s->parity = parity;
+      s->launches = launches;
+      cudaMemcpyAsync(s->u, su, bytes, cudaMemcpyDeviceToDevice, s->stream);
+      cudaMemcpyAsync(s->v, sv, bytes, cudaMemcpyDeviceToDevice, s->stream);
+      cudaStreamSynchronize(s->stream);
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
+    if (su) cudaFree(su);
+    if (sv) cudaFree(sv);
+    cudaGetLastError();
+  }
+  s->plan_variant = cands[best].variant;
+  s->plan_T = cands[best].T;
+  s->plan_iterations = iterations;
+  return SAYAL_OK;
+}
+
+int launch_projection_tiled(Sim* s, int iterations, float d_t) {
+  if (s->ph.enable_pressure) return launch_projection_plain(s, iterations, d_t);  // pressure accumulates per cell: plain path
+  int r = tiled_prepare(s, iterations);
+  if (r != SAYAL_OK) return r;
+  return run_passes(s, s->plan_variant, s->plan_T, iterations);
 }
 
 }  // namespace sayal

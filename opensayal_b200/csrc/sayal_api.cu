@@ -125,6 +125,9 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   s->projection_kernel = 1;
   s->temporal_block = 0;  // 0 = auto
   s->use_graph = 1;
+  s->autotune = 1;
+  s->plan_variant = -1;
+  s->force_variant = -1;
 
   auto fail = [&](int code) {
     free_sim(s);
@@ -139,8 +142,10 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
     if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
     cudaMemsetAsync(*f, 0, bytes, s->stream);
   }
-  e = cudaMalloc(&s->flags, field_elems(s));
+  // + slack marked solid: the tap (W, j) of the last row reads one byte past the array when pitch == W
+  e = cudaMalloc(&s->flags, field_elems(s) + 64);
   if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
+  cudaMemsetAsync(s->flags, FL_SOLID, field_elems(s) + 64, s->stream);
   e = cudaMalloc(&s->d_range, 2 * sizeof(int32_t));
   if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
   e = cudaMalloc(&s->d_overflow, sizeof(int32_t));
@@ -247,6 +252,7 @@ int sayal_run(sayal_sim* sim, int32_t steps, float d_t) {
     invalidate_graphs(s);
     s->graph_dt = d_t;
   }
+  if (s->projection_kernel == 1) TRY(tiled_prepare(s, s->cfg.proj_n));  // timing is not capturable
   int remaining = steps;
   // One graph per starting parity holds ONE step; replaying it is followed by the same pointer swaps on
   // the host that capture performed, so the next replay (or eager call) sees the right front buffers.
@@ -454,6 +460,14 @@ int sayal_set_option(sayal_sim* sim, const char* key, int64_t value) {
   } else if (!strcmp(key, "temporal_block")) {
     if (value < 0 || value > tiled_max_temporal_block()) return set_error(SAYAL_EINVAL, "temporal_block out of range");
     s->temporal_block = (int)value;
+    s->plan_variant = -1;
+  } else if (!strcmp(key, "tile_rows_per_warp")) {  // 0 = any, else 8 / 10 / 12
+    if (value != 0 && value != 8 && value != 10 && value != 12) return set_error(SAYAL_EINVAL, "tile_rows_per_warp must be 0, 8, 10 or 12");
+    s->force_variant = value == 0 ? -1 : (int)(value - 8) / 2;
+    s->plan_variant = -1;
+  } else if (!strcmp(key, "autotune")) {
+    s->autotune = value != 0;
+    s->plan_variant = -1;
   } else if (!strcmp(key, "use_graph")) {
     s->use_graph = value != 0;
   } else {
@@ -468,6 +482,9 @@ int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value) {
   if (!strcmp(key, "projection_kernel")) *value = s->projection_kernel;
   else if (!strcmp(key, "temporal_block")) *value = s->temporal_block;
   else if (!strcmp(key, "use_graph")) *value = s->use_graph;
+  else if (!strcmp(key, "autotune")) *value = s->autotune;
+  else if (!strcmp(key, "plan_temporal_block")) *value = s->plan_variant >= 0 ? s->plan_T : 0;
+  else if (!strcmp(key, "plan_rows_per_warp")) *value = s->plan_variant >= 0 ? 8 + 2 * s->plan_variant : 0;
   else if (!strcmp(key, "halo_overflow")) {
     int32_t v = 0;
     CUDA_TRY(cudaSetDevice(s->device));

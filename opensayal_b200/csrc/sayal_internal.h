@@ -71,6 +71,9 @@ struct Sim {
   int temporal_block;     // iterations per pass of the tiled kernel
   int use_graph;
   int fuse_forces;
+  int autotune;           // time candidate tile plans on first use
+  int force_variant;      // -1 = any tile variant
+  int plan_variant, plan_T, plan_iterations;  // chosen tile plan (projection_tile.cu)
   // CUDA graph cache for sayal_run: one single-step graph per starting buffer parity, with the
   // pointer assignment the step leaves behind (the step swaps front and back buffers)
   cudaGraphExec_t graph[4];   // indexed by `parity`
@@ -96,6 +99,7 @@ int launch_pack_rows(Sim* s, int local_row0, int nrows, int field_mask, float* d
 // ---- projection_tile.cu --------------------------------------------------------------------------
 int launch_projection_tiled(Sim* s, int iterations, float d_t);
 int tiled_max_temporal_block();
+int tiled_prepare(Sim* s, int iterations);  // choose the tile plan (may time candidates; not capturable)
 
 }  // namespace sayal
 

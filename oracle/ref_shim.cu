@@ -12,8 +12,8 @@
  * the GPU box, (2) time the reference on the same B200 (bench.py --impl reference).
  */
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
-#include <malloc.h>
 #include <new>
 
 #include <cuda_runtime.h>
@@ -81,13 +81,15 @@ static float* field_ptr(ref_sim* s, int field) {
 
 extern "C" {
 
+/* H2: Fluid::init_device_memory malloc()s total_s and only ever ++'s it (fluid.cu:102-103, 127-142), so the
+ * reference is correct only when malloc returns fresh zero pages — true in its own short-lived process, not in
+ * a long-lived test process whose heap holds dirty free chunks (observed on the GPU box: garbage total_s and a
+ * 6e-2 error in u).  oracle/Makefile links this library with -Wl,--wrap=malloc, which redirects the malloc
+ * calls of the objects linked here (the reference's fluid.o among them, unmodified) to this zeroing version. */
+void* __wrap_malloc(size_t n) { return std::calloc(1, n ? n : 1); }
+
 int ref_create(const sayal_config* c, int device, ref_sim** out) {
   if (cudaSetDevice(device) != cudaSuccess) return SAYAL_ECUDA;
-  /* H2: Fluid::init_device_memory malloc()s total_s and only ever ++'s it (fluid.cu:102-103, 127-142), so the
-   * reference is correct only when malloc hands out fresh zero pages.  In a long-lived test process glibc's
-   * dynamic mmap threshold grows and recycles dirty heap memory instead.  Pin the threshold so that every
-   * allocation of the size of a field is a fresh mmap, as it is in the reference's own short-lived process. */
-  mallopt(M_MMAP_THRESHOLD, 16 * 1024);
   ref_sim* s = new (std::nothrow) ref_sim();
   if (!s) return SAYAL_ENOMEM;
   s->W = c->width;

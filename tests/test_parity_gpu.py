@@ -92,13 +92,16 @@ def test_projection_bit_exact(name, kernel):
     assert_same(gpu, cpu, names=("u", "v"), what=f"projection kernel={kernel}")
 
 
+@pytest.mark.parametrize("rows", [8, 10, 12])
 @pytest.mark.parametrize("T", [1, 2, 3, 4, 5, 8, 12])
-def test_tiled_projection_any_temporal_block(T):
-    """Tiling / temporal blocking must not change a bit: several tiles in x and y, n not divisible by T."""
+def test_tiled_projection_any_temporal_block(T, rows):
+    """Tiling / temporal blocking must not change a bit: several tiles in x and y, n not divisible by T,
+    every tile variant (rows per warp)."""
     cfg = baseline_config(1, width=520, height=470)
     gpu, cpu = pair(cfg)
     gpu.set_option("projection_kernel", 1)
     gpu.set_option("temporal_block", T)
+    gpu.set_option("tile_rows_per_warp", rows)
     gpu.stage_projection(13, 0.05)
     cpu.projection(13, 0.05)
     assert_same(gpu, cpu, names=("u", "v"), what=f"tiled T={T}")
@@ -204,6 +207,32 @@ def test_run_equals_repeated_update(graph):
         b.update(None)
     assert np.array_equal(a.get_field("u"), b.get_field("u"))
     assert a.launch_count == b.launch_count
+
+
+def test_autotuned_plan_is_invisible():
+    """The autotuner times candidate plans on the live arrays; state, results and launch count must not show it."""
+    cfg = baseline_config(1, width=640, height=400)
+    a, cpu = pair(cfg)
+    b, _ = pair(cfg)
+    b.set_option("autotune", 0)
+    a.stage_projection(50, 0.05)
+    b.stage_projection(50, 0.05)
+    cpu.projection(50, 0.05)
+    assert_same(a, cpu, names=("u", "v"), what="autotuned")
+    assert_same(b, cpu, names=("u", "v"), what="model plan")
+    assert a.get_option("plan_temporal_block") >= 1 and a.get_option("plan_rows_per_warp") in (8, 10, 12)
+
+
+def test_cell_size_2_generic_path():
+    """Integer cell_size != 1 takes the generic (HC = 0) advection kernels and the hf pressure multiply."""
+    cfg = baseline_config(0, width=160, height=120)
+    cfg["sim.cell_size"] = 2.0
+    cfg["sim.projection.n"] = 6
+    gpu, cpu = pair(cfg)
+    for _ in range(2):
+        gpu.update(None)
+        cpu.step(None)
+    assert_same(gpu, cpu, names=("u", "v", "smoke", "p"), what="cell_size 2")
 
 
 def test_zero_start_wind_tunnel_matches_oracle():
