@@ -258,7 +258,10 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_tile_kernel(TileArgs a)
   {
     const unsigned open_a = (unsigned)FL_OPEN | ((unsigned)FL_OPEN << 16);
     const unsigned open_b = ((unsigned)FL_OPEN << 8) | ((unsigned)FL_OPEN << 24);
-    const unsigned mask_b = lane == 31 ? 0x0000ff00u : 0xff00ff00u;  // the carrier column may compute garbage
+    // The carrier column may compute garbage in the open path — but only where it is halo, i.e. the tile has a
+    // right neighbour.  A tile that ends exactly on the last column keeps the test (that column is a border
+    // cell, so its rows take the general path).
+    const unsigned mask_b = (lane == 31 && X0 + TW < g.pitch) ? 0x0000ff00u : 0xff00ff00u;
 #pragma unroll
     for (int r = 0; r < RY; r++) {
       bool oka = (fl[r] & 0x00ff00ffu) == open_a;

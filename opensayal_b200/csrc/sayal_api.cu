@@ -1,6 +1,7 @@
 // sayal_api.cu — the C ABI of include/sayal.h over the CUDA step path.  Host-side mirror of
 // Fluid::Fluid / ~Fluid / update (/root/reference/src/fluid.cu:41-97, 770-795).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -128,6 +129,13 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   s->autotune = 1;
   s->plan_variant = -1;
   s->force_variant = -1;
+  // experiment / profiling overrides (never change results): SAYAL_AUTOTUNE=0, SAYAL_TEMPORAL_BLOCK=T,
+  // SAYAL_TILE_ROWS=8|10|12, SAYAL_PROJECTION_KERNEL=0|1, SAYAL_USE_GRAPH=0|1
+  if (const char* e = getenv("SAYAL_AUTOTUNE")) s->autotune = atoi(e) != 0;
+  if (const char* e = getenv("SAYAL_TEMPORAL_BLOCK")) { int t = atoi(e); if (t >= 0 && t <= tiled_max_temporal_block()) s->temporal_block = t; }
+  if (const char* e = getenv("SAYAL_TILE_ROWS")) { int r = atoi(e); if (r == 8 || r == 10 || r == 12) s->force_variant = (r - 8) / 2; }
+  if (const char* e = getenv("SAYAL_PROJECTION_KERNEL")) s->projection_kernel = atoi(e) != 0;
+  if (const char* e = getenv("SAYAL_USE_GRAPH")) s->use_graph = atoi(e) != 0;
 
   auto fail = [&](int code) {
     free_sim(s);

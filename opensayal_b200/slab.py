@@ -1,0 +1,339 @@
+"""Multi-GPU y-slabs for the step path.  No reference equivalent: OpenSayal is single-GPU.
+
+Memory rows are y (index = (H-1-j)*W + i, fluid.cu:163-165), so a slab is one contiguous row range.  Rank k of
+N owns rows [k*H/N, (k+1)*H/N) and keeps `halo` ghost rows of every field on each interior side.
+
+Why ghost rows are enough (and keep the result bit-identical to one GPU):
+  * projection (fluid.cu:229-262): a half-sweep has dependency radius one row, so after k iterations the ghost
+    rows are wrong only within 2k rows of the local array edge.  With halo >= 2k the owned rows stay exact for
+    k iterations; then neighbours swap edge rows.  `iters_per_exchange = halo // 2`.  The update is
+    order-independent within a colour, so the owned rows hold the same bits as the single-GPU sweep.
+  * advection (fluid.cu:560-617) is a gather: exact as long as the back-trace stays inside the ghost rows.  The
+    kernels count every sample that would leave them (`halo_overflow`); a non-zero count is an error.
+  * forces / extrapolation are functions of position and of the local neighbour row: applied to every held row.
+
+Per step: forces, [projection chunk, exchange(u,v)] x ceil(n / iters_per_exchange), extrapolation, velocity
+advection, exchange(u,v), smoke advection, exchange(smoke).  The exchange itself is a neighbour send/recv of
+`halo` packed rows (NCCL over NVLink between processes, a device copy between slabs of one process).
+
+The schedule is data (a list of ops), so the same program drives real slabs over torch.distributed, several
+slabs on one GPU (tests) and a numpy stand-in under gloo on CPU (tests of the host logic).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+F_U, F_V, F_SMOKE, F_P = 1, 2, 4, 8
+
+
+def slab_rows(height: int, world: int, rank: int) -> Tuple[int, int]:
+    """(row0, rows) of rank's slab: contiguous memory rows, remainder spread over the first ranks."""
+    base, extra = divmod(height, world)
+    rows = base + (1 if rank < extra else 0)
+    row0 = rank * base + min(rank, extra)
+    return row0, rows
+
+
+def step_schedule(n_iterations: int, halo: int, pressure: bool, smoke: bool) -> List[tuple]:
+    """One Fluid::update (fluid.cu:770-795) as slab operations."""
+    if halo < 2:
+        raise ValueError("halo must be >= 2 rows (one SOR iteration reaches two rows)")
+    per = halo // 2
+    ops: List[tuple] = [("forces",)]
+    if pressure:
+        ops.append(("zero_pressure",))
+    done = 0
+    while done < n_iterations:
+        k = min(per, n_iterations - done)
+        ops.append(("projection", k))
+        ops.append(("exchange", F_U | F_V))
+        done += k
+    if pressure:
+        ops.append(("pressure_range",))
+    ops.append(("extrapolation",))
+    ops.append(("advect_velocity",))
+    ops.append(("exchange", F_U | F_V))
+    if smoke:
+        ops.append(("advect_smoke",))
+        ops.append(("exchange", F_SMOKE))
+    return ops
+
+
+def n_fields(mask: int) -> int:
+    return bin(mask & 0xF).count("1")
+
+
+class FluidSlab:
+    """Adapter: one opensayal_b200.Fluid slab + its torch pack buffers."""
+
+    def __init__(self, cfg, device: int, row0: int, rows: int, halo: int, first: bool, last: bool):
+        import torch
+
+        from .fluid import Fluid
+        self.torch = torch
+        self.sim = Fluid(cfg, device=device, slab=(row0, rows, halo))
+        self.device = torch.device("cuda", device)
+        self.halo, self.width, self.rows, self.row0 = halo, cfg.c.width, rows, row0
+        self.first, self.last = first, last  # no neighbour on the low-row / high-row side
+        n = halo * cfg.c.width * 3
+        with torch.cuda.device(self.device):
+            self.send = [torch.empty(n, dtype=torch.float32, device=self.device) for _ in range(2)]
+            self.recv = [torch.empty(n, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.stream = torch.cuda.ExternalStream(self.sim.stream, device=self.device)
+        self.d_t = cfg.c.d_t
+
+    # ---- stages -------------------------------------------------------------------------------
+    def apply(self, op: tuple, source=None, d_t: Optional[float] = None):
+        d_t = self.d_t if d_t is None else d_t
+        s = self.sim
+        kind = op[0]
+        if kind == "forces":
+            s.stage_forces(source, d_t)
+        elif kind == "zero_pressure":
+            s.stage_zero_pressure()
+        elif kind == "projection":
+            s.stage_projection(op[1], d_t)
+        elif kind == "pressure_range":
+            pass  # stage_projection already queued the local range; the global one is an all-reduce (pressure_range())
+        elif kind == "extrapolation":
+            s.stage_extrapolation()
+        elif kind == "advect_velocity":
+            s.stage_advect_velocity(d_t)
+        elif kind == "advect_smoke":
+            s.stage_advect_smoke(d_t)
+        else:
+            raise ValueError(op)
+
+    def pack(self, side: int, mask: int):
+        self.sim.pack_edge(side, self.halo, mask, self.send[side].data_ptr())
+        return self.send[side][: self.halo * self.width * n_fields(mask)]
+
+    def recv_buffer(self, side: int, mask: int):
+        return self.recv[side][: self.halo * self.width * n_fields(mask)]
+
+    def unpack(self, side: int, mask: int):
+        self.sim.unpack_ghost(side, self.halo, mask, self.recv[side].data_ptr())
+
+    def close(self):
+        self.sim.close()
+
+
+def exchange_local(slabs: Sequence, mask: int) -> None:
+    """Neighbour exchange between slabs living in ONE process (tests; single-GPU emulation)."""
+    for a, b in zip(slabs[:-1], slabs[1:]):  # a is above b: a's high-row edge <-> b's low-row ghost
+        src = a.pack(1, mask)
+        dst = b.recv_buffer(0, mask)
+        _copy(a, b, dst, src)
+        b.unpack(0, mask)
+        src = b.pack(0, mask)
+        dst = a.recv_buffer(1, mask)
+        _copy(b, a, dst, src)
+        a.unpack(1, mask)
+
+
+def _copy(src_slab, dst_slab, dst, src):
+    torch = getattr(src_slab, "torch", None)
+    if torch is not None and src.is_cuda:
+        # order: packed on src stream -> copy -> unpack on dst stream
+        ev = torch.cuda.Event()
+        ev.record(src_slab.stream)
+        dst_slab.stream.wait_event(ev)
+        with torch.cuda.stream(dst_slab.stream):
+            dst.copy_(src, non_blocking=True)
+    else:
+        dst[...] = src
+
+
+def exchange_dist(slab, mask: int, rank: int, world: int, group=None) -> None:
+    """Neighbour exchange over torch.distributed (NCCL between GPUs; gloo in the CPU tests)."""
+    import torch.distributed as dist
+    ops = []
+    torch = getattr(slab, "torch", None)
+    ctx = torch.cuda.stream(slab.stream) if torch is not None and getattr(slab, "stream", None) is not None else _null()
+    with ctx:
+        if rank > 0:
+            ops.append(dist.P2POp(dist.isend, slab.pack(0, mask), rank - 1, group))
+            ops.append(dist.P2POp(dist.irecv, slab.recv_buffer(0, mask), rank - 1, group))
+        if rank < world - 1:
+            ops.append(dist.P2POp(dist.isend, slab.pack(1, mask), rank + 1, group))
+            ops.append(dist.P2POp(dist.irecv, slab.recv_buffer(1, mask), rank + 1, group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        if rank > 0:
+            slab.unpack(0, mask)
+        if rank < world - 1:
+            slab.unpack(1, mask)
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def run_schedule_local(slabs: Sequence, ops: Sequence[tuple], source=None, d_t=None) -> None:
+    for op in ops:
+        if op[0] == "exchange":
+            exchange_local(slabs, op[1])
+        else:
+            for s in slabs:
+                s.apply(op, source, d_t)
+
+
+def run_schedule_dist(slab, ops: Sequence[tuple], rank: int, world: int, source=None, d_t=None, group=None) -> None:
+    for op in ops:
+        if op[0] == "exchange":
+            exchange_dist(slab, op[1], rank, world, group)
+        else:
+            slab.apply(op, source, d_t)
+
+
+class SlabFluid:
+    """`Fluid` over N y-slabs, one process per slab (torch.distributed must be initialised)."""
+
+    def __init__(self, cfg, rank: int, world: int, device: int, halo: int = 16, group=None):
+        self.cfg, self.rank, self.world, self.group = cfg, rank, world, group
+        c = cfg.c
+        row0, rows = slab_rows(c.height, world, rank)
+        if world > 1 and rows < halo:
+            raise ValueError(f"slab of {rows} rows is thinner than the halo ({halo})")
+        self.row0, self.rows, self.halo = row0, rows, halo
+        self.slab = FluidSlab(cfg, device, row0, rows, halo if world > 1 else 0, rank == 0, rank == world - 1)
+        self.ops = step_schedule(c.proj_n, halo, bool(c.enable_pressure), bool(c.enable_smoke) and c.wt_smoke != 0) \
+            if world > 1 else None
+
+    @property
+    def sim(self):
+        return self.slab.sim
+
+    def set_initial(self, u, v, smoke) -> None:
+        """Owned rows of each field (rows x W); ghosts are filled by an exchange."""
+        self.sim.set_field("u", u)
+        self.sim.set_field("v", v)
+        self.sim.set_field("smoke", smoke)
+        if self.world > 1:
+            exchange_dist(self.slab, F_U | F_V | F_SMOKE, self.rank, self.world, self.group)
+
+    def update(self, source=None, d_t=None) -> None:
+        if self.world == 1:
+            self.sim.step_async(source, d_t)
+        else:
+            run_schedule_dist(self.slab, self.ops, self.rank, self.world, source, d_t, self.group)
+
+    def sync(self) -> None:
+        self.sim.sync()
+
+    def halo_overflow(self) -> int:
+        return self.sim.get_option("halo_overflow")
+
+    def pressure_range(self):
+        import torch
+        import torch.distributed as dist
+        mn, mx = self.sim.min_pressure, self.sim.max_pressure
+        if self.world == 1:
+            return mn, mx
+        t = torch.tensor([mn, -mx], dtype=torch.float32, device=self.slab.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return float(t[0]), float(-t[1])
+
+    def close(self):
+        self.slab.close()
+
+
+# ----------------------------------------------------------------------------------------------------
+def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSampler, measured_hbm_peak: Callable,
+                algorithmic_bytes_per_cell_step: Callable):
+    """bench.py's N > 1 leg: weak scaling, one rank per GPU, launched by torch.distributed.run."""
+    import os
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    from .synthetic import synthetic_fields
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1:
+        raise SystemExit("bench.py --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = workload_config(world)
+    c = cfg.c
+    halo = int(os.environ.get("SAYAL_SLAB_HALO", "32"))
+    sf = SlabFluid(cfg, rank, world, local, halo=halo)
+    u, v, sm = synthetic_fields(c.width, c.height, rows=(sf.row0, sf.rows))
+    sf.set_initial(u, v, sm)
+    stream = sf.slab.stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        sf.update()
+    sf.sync()
+    dist.barrier()
+    torch.cuda.synchronize()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches0 = sf.sim.launch_count
+    with ClockSampler(local) as clocks:
+        for k in range(args.steps):
+            with torch.cuda.stream(stream):
+                flush.fill_(1)
+            starts[k].record(stream)
+            sf.update()
+            stops[k].record(stream)
+        sf.sync()
+        torch.cuda.synchronize()
+        dist.barrier()
+    launches = sf.sim.launch_count - launches0
+    ms_local = sum(s.elapsed_time(e) for s, e in zip(starts, stops)) / args.steps
+    t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    overflow = torch.tensor([sf.halo_overflow()], dtype=torch.int64, device="cuda")
+    dist.all_reduce(overflow, op=dist.ReduceOp.SUM)
+    cells = c.width * c.height
+    value = cells / (ms * 1e-3)
+
+    # end to end: owned rows from pinned host buffers, K steps, owned rows back — wall clock, max over ranks
+    pinned = {k: torch.from_numpy(a).pin_memory() for k, a in (("u", u), ("v", v), ("smoke", sm))}
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sf.set_initial(pinned["u"].numpy(), pinned["v"].numpy(), pinned["smoke"].numpy())
+    for _ in range(args.steps):
+        sf.update()
+    outs = [sf.sim.get_field(n) for n in ("u", "v", "smoke")]
+    t1 = time.perf_counter()
+    te = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = cells * args.steps / float(te[0])
+    field_bytes = 3 * cells * 4
+    launches_t = torch.tensor([launches], dtype=torch.int64, device="cuda")
+    dist.all_reduce(launches_t, op=dist.ReduceOp.SUM)
+    peak, peak_src = measured_hbm_peak()
+    b_alg = algorithmic_bytes_per_cell_step(c.proj_n, int(bool(c.enable_pressure)), 1)
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "cell-steps/sec (n=50 SOR)", "value": value, "unit": "cell-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_block(cfg, world, {"halo_rows": halo, "exchange": "NCCL send/recv of packed edge rows",
+                                                "halo_overflow": int(overflow[0])}),
+            "roofline": {"bound": "hbm", "kernel": "whole step, all GPUs", "achieved": round(value * b_alg / 1e9, 1),
+                         "peak": peak * world, "unit": "GB/s", "frac": round(value * b_alg / 1e9 / (peak * world), 4),
+                         "traffic": None, "peak_source": peak_src + f" x {world} GPUs"},
+            "cpu_baseline": None,
+            "e2e": {"value": e2e_value, "unit": "cell-steps/s", "h2d_bytes_per_step": field_bytes / args.steps + 20,
+                    "d2h_bytes_per_step": field_bytes / args.steps},
+            "gpu_launches": int(launches_t[0]), "clocks": clocks.summary(),
+        }
+    sf.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    return line

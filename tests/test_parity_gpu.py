@@ -93,7 +93,7 @@ def test_projection_bit_exact(name, kernel):
 
 
 @pytest.mark.parametrize("rows", [8, 10, 12])
-@pytest.mark.parametrize("T", [1, 2, 3, 4, 5, 8, 12])
+@pytest.mark.parametrize("T", [1, 2, 3, 4, 5, 8, 12, 16])
 def test_tiled_projection_any_temporal_block(T, rows):
     """Tiling / temporal blocking must not change a bit: several tiles in x and y, n not divisible by T,
     every tile variant (rows per warp)."""
@@ -207,6 +207,18 @@ def test_run_equals_repeated_update(graph):
         b.update(None)
     assert np.array_equal(a.get_field("u"), b.get_field("u"))
     assert a.launch_count == b.launch_count
+
+
+@pytest.mark.parametrize("width,T", [(352, 3), (352, 4), (384, 15), (384, 16), (336, 5), (336, 6), (1920, 4)])
+def test_tile_ending_exactly_on_the_last_column(width, T):
+    """Regression: when 128 + k*stride == W the last tile has no right halo; its carrier column is the real
+    border column and must not take the all-open path (found by the slab test at T=16)."""
+    cfg = baseline_config(1, width=width, height=200)
+    gpu, cpu = pair(cfg)
+    gpu.set_option("temporal_block", T)
+    gpu.stage_projection(2 * T + 1, 0.05)
+    cpu.projection(2 * T + 1, 0.05)
+    assert_same(gpu, cpu, names=("u", "v"), what=f"exact fit W={width} T={T}")
 
 
 def test_autotuned_plan_is_invisible():

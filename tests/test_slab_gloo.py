@@ -1,0 +1,198 @@
+"""Host-side logic of the y-slab driver (opensayal_b200/slab.py) on CPU: world_size-2 and -3 `gloo` process
+groups exchanging ghost rows of a numpy stand-in whose operations have the same dependency reach as the real
+stages (projection: one row per half-sweep; advection: a bounded gather).  The result must equal the
+single-domain run exactly — it does only if the schedule exchanges often enough and addresses the right rows.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from opensayal_b200 import slab as S
+
+W, H, N_ITER, REACH = 24, 61, 7, 3
+
+
+class NumpySlab:
+    """Stand-in for FluidSlab: local rows [lo, hi) of a global H-row domain, ghost rows included."""
+
+    def __init__(self, full, row0, rows, halo, first, last):
+        self.row0, self.rows, self.halo, self.first, self.last = row0, rows, halo, first, last
+        self.lo = row0 - (0 if first else halo)
+        self.hi = row0 + rows + (0 if last else halo)
+        self.f = {k: a[self.lo:self.hi].copy() for k, a in full.items()}  # ghosts start fresh
+        self.width = W
+        n = halo * W * 3
+        self.send = [torch.empty(n, dtype=torch.float32) for _ in range(2)]
+        self.recv = [torch.empty(n, dtype=torch.float32) for _ in range(2)]
+
+    def _names(self, mask):
+        return [n for bit, n in ((S.F_U, "u"), (S.F_V, "v"), (S.F_SMOKE, "smoke")) if mask & bit]
+
+    def apply(self, op, source=None, d_t=None):
+        kind = op[0]
+        g = np.arange(self.lo, self.hi)[:, None]  # global row of every local row
+        if kind == "forces":
+            self.f["v"] += (0.01 * g).astype(np.float32)
+        elif kind == "projection":
+            for _ in range(op[1]):
+                for colour in (0, 1):
+                    for name in ("u", "v"):
+                        a = self.f[name]
+                        new = a.copy()
+                        for lr in range(len(a)):
+                            r = self.lo + lr
+                            if r == 0 or r == H - 1 or (r + colour) % 2:
+                                continue
+                            up = a[lr - 1] if lr > 0 else 0.0          # missing neighbour => wrong, like a ghost edge
+                            dn = a[lr + 1] if lr + 1 < len(a) else 0.0
+                            new[lr] = np.float32(0.5) * a[lr] + np.float32(0.25) * (up + dn)
+                        self.f[name] = new
+        elif kind in ("advect_velocity", "advect_smoke"):
+            names = ("u", "v") if kind == "advect_velocity" else ("smoke",)
+            own0 = self.row0 - self.lo
+            for name in names:
+                a = self.f[name]
+                new = a.copy()
+                for lr in range(own0, own0 + self.rows):  # owned rows only
+                    r = self.lo + lr
+                    for i in range(W):
+                        src = min(max(r + (i % (2 * REACH + 1)) - REACH, 0), H - 1)
+                        assert self.lo <= src < self.hi, "back-trace left the ghost rows"
+                        new[lr, i] = a[src - self.lo, i]
+                self.f[name] = new
+        elif kind in ("extrapolation", "zero_pressure", "pressure_range"):
+            pass
+        else:
+            raise ValueError(op)
+
+    def pack(self, side, mask):
+        own0 = self.row0 - self.lo
+        rows = slice(own0, own0 + self.halo) if side == 0 else slice(own0 + self.rows - self.halo, own0 + self.rows)
+        flat = np.concatenate([self.f[n][rows].ravel() for n in self._names(mask)])
+        self.send[side][: flat.size] = torch.from_numpy(flat)
+        return self.send[side][: flat.size]
+
+    def recv_buffer(self, side, mask):
+        return self.recv[side][: self.halo * W * len(self._names(mask))]
+
+    def unpack(self, side, mask):
+        own0 = self.row0 - self.lo
+        rows = slice(own0 - self.halo, own0) if side == 0 else slice(own0 + self.rows, own0 + self.rows + self.halo)
+        buf = self.recv[side].numpy()
+        for k, n in enumerate(self._names(mask)):
+            self.f[n][rows] = buf[k * self.halo * W:(k + 1) * self.halo * W].reshape(self.halo, W)
+
+    def owned(self, name):
+        own0 = self.row0 - self.lo
+        return self.f[name][own0:own0 + self.rows]
+
+
+def initial():
+    rng = np.random.default_rng(3)
+    return {k: rng.standard_normal((H, W)).astype(np.float32) for k in ("u", "v", "smoke")}
+
+
+def single_domain(steps):
+    s = NumpySlab(initial(), 0, H, 0, True, True)
+    ops = [op for op in S.step_schedule(N_ITER, 8, False, True) if op[0] != "exchange"]
+    for _ in range(steps):
+        for op in ops:
+            s.apply(op)
+    return s.f
+
+
+def test_slab_rows_partition():
+    for height, world in ((1080, 8), (61, 3), (16384, 8), (10, 4)):
+        spans = [S.slab_rows(height, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and sum(n for _, n in spans) == height
+        for (a0, an), (b0, _) in zip(spans[:-1], spans[1:]):
+            assert a0 + an == b0
+        assert max(n for _, n in spans) - min(n for _, n in spans) <= 1
+
+
+def test_schedule_shape():
+    ops = S.step_schedule(50, 16, False, True)
+    assert ops[0] == ("forces",)
+    proj = [op for op in ops if op[0] == "projection"]
+    assert sum(k for _, k in proj) == 50 and all(k <= 8 for _, k in proj)
+    # every projection chunk is followed by an exchange of u and v
+    for idx, op in enumerate(ops):
+        if op[0] == "projection":
+            assert ops[idx + 1] == ("exchange", S.F_U | S.F_V)
+    assert ops[-1] == ("exchange", S.F_SMOKE) and ops[-2] == ("advect_smoke",)
+    assert ("zero_pressure",) in S.step_schedule(4, 4, True, False)
+    with pytest.raises(ValueError):
+        S.step_schedule(4, 1, False, False)
+
+
+@pytest.mark.parametrize("world,halo", [(2, 4), (3, 6), (4, 5)])
+def test_local_exchange_matches_single_domain(world, halo):
+    full = initial()
+    slabs = []
+    for r in range(world):
+        row0, rows = S.slab_rows(H, world, r)
+        slabs.append(NumpySlab(full, row0, rows, halo, r == 0, r == world - 1))
+    ops = S.step_schedule(N_ITER, halo, False, True)
+    for _ in range(3):
+        S.run_schedule_local(slabs, ops)
+    want = single_domain(3)
+    for s in slabs:
+        for name in ("u", "v", "smoke"):
+            assert np.array_equal(s.owned(name), want[name][s.row0:s.row0 + s.rows]), (name, s.row0)
+
+
+def test_too_thin_halo_is_detected_by_this_test_design():
+    """Sanity of the stand-in: exchanging too rarely (halo claims 8, schedule thinks 16) must change results."""
+    full = initial()
+    slabs = []
+    for r in range(2):
+        row0, rows = S.slab_rows(H, 2, r)
+        slabs.append(NumpySlab(full, row0, rows, 4, r == 0, r == 1))
+    ops = S.step_schedule(N_ITER, 16, False, True)  # schedule for a deeper halo than the slabs hold
+    S.run_schedule_local(slabs, ops)
+    want = single_domain(1)
+    assert any(not np.array_equal(s.owned("u"), want["u"][s.row0:s.row0 + s.rows]) for s in slabs)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, halo, steps, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        row0, rows = S.slab_rows(H, world, rank)
+        s = NumpySlab(initial(), row0, rows, halo, rank == 0, rank == world - 1)
+        ops = S.step_schedule(N_ITER, halo, False, True)
+        for _ in range(steps):
+            S.run_schedule_dist(s, ops, rank, world)
+        out[rank] = {n: s.owned(n).copy() for n in ("u", "v", "smoke")}
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_exchange_matches_single_domain(world):
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        out = mgr.dict()
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, 6, 2, out)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0
+        want = single_domain(2)
+        for r in range(world):
+            row0, rows = S.slab_rows(H, world, r)
+            for name in ("u", "v", "smoke"):
+                assert np.array_equal(out[r][name], want[name][row0:row0 + rows]), (r, name)
