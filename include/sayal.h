@@ -167,6 +167,9 @@ int sayal_stage_advect_smoke(sayal_sim* sim, float d_t);
  * "plan_rows_per_warp", "halo_overflow", "pitch", "local_rows", "own_lo", "own_hi".  No option changes results. */
 int sayal_set_option(sayal_sim* sim, const char* key, int64_t value);
 int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value);
+/* Profiling only (option "debug_timeline" = 1): per-CTA timestamps of the last projection pass, 5 int64 per tile
+ * {entry, tile loaded, sweeps done, stores issued (globaltimer ns), SM id}. */
+int sayal_debug_timeline(sayal_sim* sim, int64_t* host_dst, int32_t max_tiles, int32_t* n_tiles);
 /* Number of kernels this library has launched on behalf of `sim` since creation. */
 int64_t sayal_launch_count(sayal_sim* sim);
 /* CUDA stream of the sim (cudaStream_t as void*), for event timing by the caller. */

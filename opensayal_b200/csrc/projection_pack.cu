@@ -1,0 +1,575 @@
+// projection_pack.cu — the pressure projection of Fluid::update (/root/reference/src/fluid.cu:229-295) as a
+// register-resident, temporally blocked red-black SOR kernel for sm_100a, second generation.
+//
+// What the reference does: 2n launches per step, each touching u, v, is_solid(int32) x5 and total_s(int32) for
+// half the cells from global memory (fluid.cu:264-295).
+//
+// What this kernel does: one launch ("pass") advances a whole tile by T full iterations (2T half-sweeps)
+// without touching global memory in between.
+//   * A CTA owns a 128-column x (NW warps * RY rows) tile.  Lane l of warp w keeps cells x = X0 + 4l .. 4l+3 of
+//     rows Y0 + w*RY .. +RY-1 in registers, as PACKED PAIRS: {u0,u2}, {u1,u3}, {v0,v2}, {v1,v3}.  The two cells
+//     of one colour in a lane are columns (0,2) or (1,3), so one Blackwell packed-fp32 instruction
+//     (add/mul/fma.rn.f32x2 -> FADD2/FMUL2/FFMA2) updates both: half the issue slots of the scalar form, same
+//     IEEE result per element.
+//   * Columns (1,3) need u of the next lane's column 0: one __shfl_down brings it, one __shfl_up returns the
+//     updated face.  Vertically adjacent warps share one row of v faces through shared memory (colour-split
+//     float2 slots, conflict-free), one barrier per half-sweep.
+//   * Cell masks without branches: the face updates of apply_projection_at (fluid.cu:247-261) are written as
+//     fma(e, m, face) with m in {+-1, 0} and the divide by total_s as a multiply by inv in {0, 1, 1/2, 1/3, 1/4}
+//     (inv = 0 switches a cell off).  Each lane keeps ONE "profile" of these multipliers (the flags of its
+//     reference row) in registers; every row whose flags equal the profile — all rows of an open tile, and all
+//     rows of a tile that only touches the left/right wall — costs exactly the same instructions as an open
+//     row.  Rows that differ (top/bottom wall, obstacle rim) fetch their multipliers from a 256-entry
+//     shared-memory table indexed by the two cells' face nibbles.  fma(e, +-1, x) == x +- e and
+//     fma(e, 0, x) == x exactly, so no bit changes with respect to the branchy form.
+//   * Tiles overlap by a halo of 2T cells (rounded up to 4 in x).  Errors from the missing neighbours travel
+//     one cell per half-sweep, so after 2T half-sweeps everything at least 2T cells inside the tile is exactly
+//     what the global sweep order produces; only that part is written, to the OTHER buffer (ping-pong).
+// The update is order-independent within a colour (cells of one colour share no face), so tiling does not
+// change a single bit: tests require equality with the plain half-sweep kernel and with the CPU oracle.
+//
+// Roofline: HBM.  Algorithmic bytes are 17 B per cell per iteration (r/w u, v + 1 flag byte); one pass moves
+// (1 + halo overhead) * 9 B in and 8 B out per cell for T iterations.
+#include <cstdio>
+
+#include "sayal_internal.h"
+
+namespace sayal {
+
+namespace {
+
+typedef unsigned long long u64;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int TW = 128;  // tile width: 32 lanes x 4 cells
+
+// ---- packed fp32 pairs (element 0 = low register) ------------------------------------------------------
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float lo(u64 v) {
+  float a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+  return a;
+}
+__device__ __forceinline__ float hi(u64 v) {
+  float a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+  return b;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+  u64 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ u64 lds64(const float* p) {
+  float2 t = *reinterpret_cast<const float2*>(p);
+  return pk(t.x, t.y);
+}
+__device__ __forceinline__ void sts64(float* p, u64 v) { *reinterpret_cast<float2*>(p) = make_float2(lo(v), hi(v)); }
+
+// The multipliers of one pair of cells.  nR / nT are stored negated: face -= e  ==  fma(e, -1, face).
+struct Mult {
+  u64 inv, mL, nR, mB, nT;
+};
+
+__device__ __forceinline__ float inv_of(unsigned nibble) {
+  int s = __popc(nibble & 15u);  // total_s of an active cell == number of open faces (build_flags_kernel)
+  return s == 0 ? 0.f : (s == 1 ? 1.0f : (s == 2 ? 0.5f : (s == 3 ? 1.0f / 3.0f : 0.25f)));
+}
+__device__ __forceinline__ float bit_pos(unsigned nibble, unsigned bit) { return (nibble & bit) ? 1.0f : 0.0f; }
+__device__ __forceinline__ float bit_neg(unsigned nibble, unsigned bit) { return (nibble & bit) ? -1.0f : 0.0f; }
+
+// Shared-memory table entry (48 B): multipliers of the cell pair with face nibbles (a, c).
+struct __align__(16) LutEntry {
+  float inv_a, inv_c, mL_a, mL_c;
+  float nR_a, nR_c, mB_a, mB_c;
+  float nT_a, nT_c, pad0, pad1;
+};
+
+__device__ __forceinline__ void lut_fill(LutEntry* e, unsigned a, unsigned c) {
+  e->inv_a = inv_of(a); e->inv_c = inv_of(c);
+  e->mL_a = bit_pos(a, FL_L); e->mL_c = bit_pos(c, FL_L);
+  e->nR_a = bit_neg(a, FL_R); e->nR_c = bit_neg(c, FL_R);
+  e->mB_a = bit_pos(a, FL_B); e->mB_c = bit_pos(c, FL_B);
+  e->nT_a = bit_neg(a, FL_T); e->nT_c = bit_neg(c, FL_T);
+  e->pad0 = e->pad1 = 0.f;
+}
+
+// byte offset of the table entry of a row's (a, c) pair: CASE 0 -> flag bytes 0 and 2, CASE 1 -> bytes 1 and 3
+__device__ __forceinline__ unsigned pair_offset(unsigned fl, int c) {
+  unsigned t = (fl >> (8 * c)) & 0x000f000fu;
+  return ((t | (t >> 12)) & 0xffu) * (unsigned)sizeof(LutEntry);
+}
+
+__device__ __forceinline__ Mult lut_load(const LutEntry* lut, unsigned byte_offset) {
+  const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(lut) + byte_offset);
+  float4 a = q[0], b = q[1];
+  float2 c = *reinterpret_cast<const float2*>(q + 2);
+  Mult m;
+  m.inv = pk(a.x, a.y); m.mL = pk(a.z, a.w);
+  m.nR = pk(b.x, b.y); m.mB = pk(b.z, b.w);
+  m.nT = pk(c.x, c.y);
+  return m;
+}
+
+struct PackArgs {
+  Grid g;
+  const float* __restrict__ u_in;
+  const float* __restrict__ v_in;
+  float* __restrict__ u_out;
+  float* __restrict__ v_out;
+  const uint8_t* __restrict__ flags;
+  float o;
+  int iters;     // iterations in this pass (<= T)
+  int halo_x;    // 2T rounded up to a multiple of 4
+  int halo_y;    // 2T
+  int stride_x;  // TW - 2*halo_x
+  int stride_y;  // TH - 2*halo_y
+  long long* timeline;  // profiling only (option "debug_timeline"): 5 x int64 per CTA, or null
+};
+
+__device__ __forceinline__ long long globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// One row of one half-sweep.  C = 0: columns (0,2) are the active colour, C = 1: columns (1,3).
+// vt / vb are the v faces above / below the row for the active columns.
+template <int C, bool MASKED>
+__device__ __forceinline__ void row_step(u64& U02, u64& U13, u64& vb, u64& vt, const Mult& m, u64 o2, int lane) {
+  if (C == 0) {
+    u64 d = sub2(add2(sub2(U13, U02), vt), vb);
+    u64 e = mul2(o2, mul2(d, m.inv));
+    U02 = fma2(e, m.mL, U02);
+    U13 = fma2(e, m.nR, U13);
+    if (MASKED) {
+      vb = fma2(e, m.mB, vb);
+      vt = fma2(e, m.nT, vt);
+    } else {
+      vb = add2(vb, e);
+      vt = sub2(vt, e);
+    }
+  } else {
+    // right faces of columns 1 and 3: own column 2 and the next lane's column 0
+    float un = __shfl_down_sync(FULL, lo(U02), 1);
+    u64 uR = pk(hi(U02), un);
+    u64 d = sub2(add2(sub2(uR, U13), vt), vb);
+    u64 e = mul2(o2, mul2(d, m.inv));
+    U13 = fma2(e, m.mL, U13);
+    uR = fma2(e, m.nR, uR);
+    if (MASKED) {
+      vb = fma2(e, m.mB, vb);
+      vt = fma2(e, m.nT, vt);
+    } else {
+      vb = add2(vb, e);
+      vt = sub2(vt, e);
+    }
+    // the updated face of the next lane's column 0 travels back; lane 0 has no left neighbour in the tile
+    float back = __shfl_up_sync(FULL, hi(uR), 1);
+    U02 = pk(lane == 0 ? lo(U02) : back, lo(uR));
+  }
+}
+
+// One half-sweep over the RY rows of this warp.  Q0 = case of row 0; the case alternates with the row.
+// IRR = false: every row uses the lane's profile multipliers.  IRR = true (a warp with at least one row that
+// differs from the profile): every row fetches its multipliers from the table; s_off holds, per row, the two
+// cases' byte offsets into it (16 bits each).  No per-row branch either way.
+template <int RY, int Q0, bool IRR>
+__device__ __forceinline__ void half_sweep(u64 (&U02)[RY], u64 (&U13)[RY], u64 (&V02)[RY - 1], u64 (&V13)[RY - 1],
+                                           const Mult (&prof)[2], u64 o2, int lane, float* sv_top, float* sv_bot,
+                                           const unsigned* s_off, const LutEntry* lut) {
+#pragma unroll
+  for (int r = 0; r < RY; r++) {
+    const int c = Q0 ^ (r & 1);
+    u64 vt, vb;
+    if (r == 0) vt = lds64(sv_top + 64 * c);
+    else vt = c ? V13[r - 1] : V02[r - 1];
+    if (r == RY - 1) vb = lds64(sv_bot + 64 * c);
+    else vb = c ? V13[r] : V02[r];
+    if (IRR) {
+      unsigned word = s_off[r * 32];
+      Mult m = lut_load(lut, c ? (word >> 16) : (word & 0xffffu));
+      if (c == 0) row_step<0, true>(U02[r], U13[r], vb, vt, m, o2, lane);
+      else row_step<1, true>(U02[r], U13[r], vb, vt, m, o2, lane);
+    } else {
+      if (c == 0) row_step<0, false>(U02[r], U13[r], vb, vt, prof[0], o2, lane);
+      else row_step<1, false>(U02[r], U13[r], vb, vt, prof[1], o2, lane);
+    }
+    if (r == 0) sts64(sv_top + 64 * c, vt);
+    else if (c) V13[r - 1] = vt;
+    else V02[r - 1] = vt;
+    if (r == RY - 1) sts64(sv_bot + 64 * c, vb);
+    else if (c) V13[r] = vb;
+    else V02[r] = vb;
+  }
+}
+
+template <int RY, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a) {
+  constexpr int TH = RY * NW;
+  // shared v rows: sv[0] is the v row above the tile (read-only halo), sv[w+1] is the last row of warp w.
+  // Layout per row: [columns (0,2): 64 floats][columns (1,3): 64 floats]; lane l owns float2 at 2l of each.
+  __shared__ __align__(16) float sv[NW + 1][128];
+  __shared__ LutEntry lut[256];
+  __shared__ unsigned s_off_all[NW][RY][32];
+
+  const Grid& g = a.g;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int X0 = blockIdx.x * a.stride_x, Y0 = blockIdx.y * a.stride_y;
+  const int x = X0 + 4 * lane;
+  const int lr0 = Y0 + w * RY;
+  long long* tl = a.timeline ? a.timeline + 5 * (size_t)(blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  if (tl && threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    tl[0] = globaltimer();
+    tl[4] = smid;
+  }
+
+  if (threadIdx.x < 256) lut_fill(&lut[threadIdx.x], threadIdx.x & 15u, threadIdx.x >> 4);
+  // Programmatic dependent launch: let the next pass's CTAs be scheduled as SMs drain, and do not read what the
+  // previous kernel wrote before it has completed.  Both are no-ops for a plain launch.
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  u64 U02[RY], U13[RY], V02[RY - 1], V13[RY - 1];
+  unsigned fl[RY];
+  u64 vlast02, vlast13;
+
+  const bool col_ok = x < g.pitch;  // pitch is a multiple of 4: a lane's four columns are in or out together
+#pragma unroll
+  for (int r = 0; r < RY; r++) {
+    int lr = lr0 + r;
+    float4 uu = make_float4(0.f, 0.f, 0.f, 0.f), vv = uu;
+    unsigned f = 0;
+    if (col_ok && lr < g.local_rows) {
+      size_t k = (size_t)lr * g.pitch + x;
+      uu = *reinterpret_cast<const float4*>(a.u_in + k);
+      vv = *reinterpret_cast<const float4*>(a.v_in + k);
+      f = *reinterpret_cast<const unsigned*>(a.flags + k);
+    }
+    U02[r] = pk(uu.x, uu.z);
+    U13[r] = pk(uu.y, uu.w);
+    if (r < RY - 1) {
+      V02[r] = pk(vv.x, vv.z);
+      V13[r] = pk(vv.y, vv.w);
+    } else {
+      vlast02 = pk(vv.x, vv.z);
+      vlast13 = pk(vv.y, vv.w);
+    }
+    fl[r] = f;
+  }
+  // The tile's last column has no column to its right: that cell only lends its faces (carrier).
+  if (lane == 31) {
+#pragma unroll
+    for (int r = 0; r < RY; r++) fl[r] &= 0x00ffffffu;
+  }
+  // The first row of a slab's local array has no row above it (its top faces are not held): carrier as well.
+  // (On a whole domain that row is the top wall, already inactive.)
+  if (lr0 == 0) fl[0] = 0;
+
+  // v faces above the tile's first row
+  float* sv_top = &sv[w][2 * lane];
+  float* sv_bot = &sv[w + 1][2 * lane];
+  sts64(sv_bot, vlast02);
+  sts64(sv_bot + 64, vlast13);
+  if (w == 0) {
+    float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col_ok && Y0 >= 1 && Y0 - 1 < g.local_rows) vv = *reinterpret_cast<const float4*>(a.v_in + (size_t)(Y0 - 1) * g.pitch + x);
+    sts64(sv_top, pk(vv.x, vv.z));
+    sts64(sv_top + 64, pk(vv.y, vv.w));
+  }
+
+  // Profile = the flags of the lane's middle row; rows that differ anywhere in the warp are irregular.
+  const unsigned pf = fl[RY / 2];
+  bool irr = false;
+  unsigned* s_off = &s_off_all[w][0][lane];
+#pragma unroll
+  for (int r = 0; r < RY; r++) {
+    if (fl[r] != pf) irr = true;
+    s_off[r * 32] = pair_offset(fl[r], 0) | (pair_offset(fl[r], 1) << 16);
+  }
+  Mult prof[2];
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    unsigned na = (pf >> (8 * c)) & 15u, nc = (pf >> (8 * c + 16)) & 15u;
+    prof[c].inv = pk(inv_of(na), inv_of(nc));
+    prof[c].mL = pk(bit_pos(na, FL_L), bit_pos(nc, FL_L));
+    prof[c].nR = pk(bit_neg(na, FL_R), bit_neg(nc, FL_R));
+    prof[c].mB = 0;
+    prof[c].nT = 0;
+  }
+  // A profile row must have all its B/T faces open for the unmasked v update to be right; if the middle row is
+  // itself next to a horizontal boundary, fall back to the table for every row that has active cells.
+  {
+    bool prof_ok = true;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      unsigned n = (pf >> (8 * k)) & 15u;
+      if (n != 0 && (n & (FL_B | FL_T)) != (FL_B | FL_T)) prof_ok = false;
+    }
+    if (!prof_ok) irr = true;
+  }
+  irr = __any_sync(FULL, irr);  // warp-uniform
+  const u64 o2 = pk(a.o, a.o);
+  __syncthreads();
+  if (tl && threadIdx.x == 0) tl[1] = globaltimer();
+
+  // Colour of column 0 in row 0 of this warp: cell (i, j) belongs to half-sweep `c` iff (i + j + c) is even
+  // (fluid.cu:266, 275).  x is a multiple of 4, so the case of row r in half-sweep c is (j0 - r + c) & 1.
+  const int j0 = g.H - 1 - (g.row_base + lr0);
+  const int q = j0 & 1;  // case of row 0 in the first (even) half-sweep: 0 -> columns (0,2)
+  static_assert(RY % 2 == 0, "rows per warp must be even: q must be uniform across the CTA's warps");
+  if (!irr) {
+    for (int it = 0; it < a.iters; it++) {
+      if (q == 0) {
+        half_sweep<RY, 0, false>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut);
+        __syncthreads();
+        half_sweep<RY, 1, false>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut);
+        __syncthreads();
+      } else {
+        half_sweep<RY, 1, false>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut);
+        __syncthreads();
+        half_sweep<RY, 0, false>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut);
+        __syncthreads();
+      }
+    }
+  } else {
+    for (int it = 0; it < a.iters; it++) {
+      if (q == 0) {
+        half_sweep<RY, 0, true>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut);
+        __syncthreads();
+        half_sweep<RY, 1, true>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut);
+        __syncthreads();
+      } else {
+        half_sweep<RY, 1, true>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut);
+        __syncthreads();
+        half_sweep<RY, 0, true>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut);
+        __syncthreads();
+      }
+    }
+  }
+
+  vlast02 = lds64(sv_bot);
+  vlast13 = lds64(sv_bot + 64);
+  if (tl && threadIdx.x == 0) tl[2] = globaltimer();
+
+  // write the part of the tile that is exact: everything >= halo away from an edge that has a neighbour
+  const int vx0 = X0 == 0 ? 0 : X0 + a.halo_x;
+  const int vx1 = X0 + TW >= g.pitch ? g.pitch : X0 + TW - a.halo_x;
+  const int vy0 = Y0 == 0 ? 0 : Y0 + a.halo_y;
+  const int vy1 = Y0 + TH >= g.local_rows ? g.local_rows : Y0 + TH - a.halo_y;
+  if (x >= vx0 && x < vx1) {
+#pragma unroll
+    for (int r = 0; r < RY; r++) {
+      int lr = lr0 + r;
+      if (lr >= vy0 && lr < vy1) {
+        size_t k = (size_t)lr * g.pitch + x;
+        *reinterpret_cast<float4*>(a.u_out + k) = make_float4(lo(U02[r]), lo(U13[r]), hi(U02[r]), hi(U13[r]));
+        u64 p02 = r < RY - 1 ? V02[r < RY - 1 ? r : 0] : vlast02;
+        u64 p13 = r < RY - 1 ? V13[r < RY - 1 ? r : 0] : vlast13;
+        *reinterpret_cast<float4*>(a.v_out + k) = make_float4(lo(p02), lo(p13), hi(p02), hi(p13));
+      }
+    }
+  }
+  if (tl) {
+    __syncthreads();
+    if (threadIdx.x == 0) tl[3] = globaltimer();
+  }
+}
+
+struct Variant {
+  int ry, nw;
+  void (*kernel)(PackArgs);
+};
+const Variant kVariants[] = {
+    {8, 16, projection_pack_kernel<8, 16>},
+    {10, 16, projection_pack_kernel<10, 16>},
+    {12, 16, projection_pack_kernel<12, 16>},
+};
+constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+constexpr int kMaxT = 16;
+
+int tiles_for(int extent, int tile, int stride) {
+  if (extent <= tile) return 1;
+  return (extent - tile + stride - 1) / stride + 1;
+}
+
+struct Geometry {
+  int halo_x, halo_y, stride_x, stride_y, tiles_x, tiles_y;
+};
+
+bool geometry(const Grid& g, const Variant& v, int T, Geometry* out) {
+  int th = v.ry * v.nw;
+  out->halo_y = 2 * T;
+  out->halo_x = (2 * T + 3) & ~3;
+  out->stride_x = TW - 2 * out->halo_x;
+  out->stride_y = th - 2 * out->halo_y;
+  if (out->stride_x < TW / 4 || out->stride_y < th / 4) return false;  // keep at least a quarter of the tile useful
+  out->tiles_x = tiles_for(g.pitch, TW, out->stride_x);
+  out->tiles_y = tiles_for(g.local_rows, th, out->stride_y);
+  return true;
+}
+
+// model of one projection of n iterations, in arbitrary units: passes x waves x (load/store + T sweeps) per row
+double model_cost(const Grid& g, const Variant& v, int T, int n, int sms) {
+  Geometry q;
+  if (!geometry(g, v, T, &q)) return 1e30;
+  int passes = (n + T - 1) / T;
+  long tiles = (long)q.tiles_x * q.tiles_y;
+  long waves = (tiles + sms - 1) / sms;
+  return (double)passes * waves * v.ry * (0.45 + 0.13 * T);
+}
+
+int run_passes(Sim* s, int variant, int T, int iterations) {
+  const Variant& v = kVariants[variant];
+  int done = 0;
+  while (done < iterations) {
+    int it = iterations - done < T ? iterations - done : T;
+    Geometry q;
+    if (!geometry(s->g, v, it, &q)) return set_error(SAYAL_EINVAL, "projection tile: temporal block too large for the tile");
+    PackArgs a;
+    a.g = s->g;
+    a.u_in = s->u;
+    a.v_in = s->v;
+    a.u_out = s->u_buf;
+    a.v_out = s->v_buf;
+    a.flags = s->flags;
+    a.o = s->ph.o;
+    a.iters = it;
+    a.halo_x = q.halo_x;
+    a.halo_y = q.halo_y;
+    a.stride_x = q.stride_x;
+    a.stride_y = q.stride_y;
+    a.timeline = s->d_timeline;  // the last pass wins: profile single passes
+    if (s->d_timeline && (size_t)q.tiles_x * q.tiles_y * 5 > s->timeline_cap) a.timeline = nullptr;
+    s->timeline_tiles = a.timeline ? q.tiles_x * q.tiles_y : 0;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(q.tiles_x, q.tiles_y);
+    lc.blockDim = dim3(v.nw * 32);
+    lc.dynamicSmemBytes = 0;
+    lc.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = s->use_pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&lc, v.kernel, a);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      char m[256];
+      snprintf(m, sizeof m, "projection_pack_kernel: %s", cudaGetErrorString(e));
+      return set_error(SAYAL_ECUDA, m);
+    }
+    s->launches++;
+    float* t = s->u; s->u = s->u_buf; s->u_buf = t;  // ping-pong: neighbouring tiles still read the old halo
+    t = s->v; s->v = s->v_buf; s->v_buf = t;
+    s->parity ^= 1;
+    done += it;
+  }
+  return SAYAL_OK;
+}
+
+}  // namespace
+
+int packed_max_temporal_block() { return kMaxT; }
+
+// Choose (tile variant, temporal block) for `iterations` SOR iterations on this grid: rank all candidates
+// with the wave-quantisation model, then time the best few on the live arrays (state saved and restored;
+// every candidate produces the same bits, so the choice never changes results).
+int packed_prepare(Sim* s, int iterations) {
+  if (s->ph.enable_pressure || iterations <= 0) return SAYAL_OK;
+  if (s->plan_iterations == iterations && s->plan_variant >= 0) return SAYAL_OK;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+  struct Cand { int variant, T; double cost; float ms; };
+  Cand cands[kNumVariants * kMaxT];
+  int nc = 0;
+  for (int v = 0; v < kNumVariants; v++)
+    for (int T = 1; T <= kMaxT && T <= iterations; T++) {
+      if (s->temporal_block > 0 && T != (s->temporal_block < iterations ? s->temporal_block : iterations)) continue;
+      if (s->force_variant >= 0 && v != s->force_variant) continue;
+      double c = model_cost(s->g, kVariants[v], T, iterations, sms);
+      if (c < 1e29) cands[nc++] = {v, T, c, 0.f};
+    }
+  if (nc == 0) return set_error(SAYAL_EINVAL, "projection tile: no feasible tile plan");
+  for (int a = 0; a < nc; a++)  // selection sort by model cost
+    for (int b = a + 1; b < nc; b++)
+      if (cands[b].cost < cands[a].cost) { Cand t = cands[a]; cands[a] = cands[b]; cands[b] = t; }
+  int best = 0;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s->stream, &cap);
+  int ntime = nc < 8 ? nc : 8;
+  if (s->autotune && cap == cudaStreamCaptureStatusNone && ntime > 1) {
+    size_t bytes = sizeof(float) * (size_t)s->g.pitch * s->g.local_rows;
+    float *su = nullptr, *sv = nullptr;
+    if (cudaMalloc(&su, bytes) == cudaSuccess && cudaMalloc(&sv, bytes) == cudaSuccess) {
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaMemcpyAsync(su, s->u, bytes, cudaMemcpyDeviceToDevice, s->stream);
+      cudaMemcpyAsync(sv, s->v, bytes, cudaMemcpyDeviceToDevice, s->stream);
+      int64_t launches = s->launches;
+      int parity = s->parity;
+      float *u0 = s->u, *v0 = s->v, *ub0 = s->u_buf, *vb0 = s->v_buf;
+      float best_ms = 1e30f;
+      for (int c = 0; c < ntime; c++) {
+        float ms_min = 1e30f;
+        for (int rep = 0; rep < 3; rep++) {  // first repetition warms the instruction cache
+          cudaEventRecord(e0, s->stream);
+          int r = run_passes(s, cands[c].variant, cands[c].T, iterations);
+          cudaEventRecord(e1, s->stream);
+          if (r != SAYAL_OK || cudaEventSynchronize(e1) != cudaSuccess) { ms_min = 1e30f; break; }
+          float ms = 0.f;
+          cudaEventElapsedTime(&ms, e0, e1);
+          if (rep > 0 && ms < ms_min) ms_min = ms;
+        }
+        cands[c].ms = ms_min;
+        if (ms_min < best_ms) { best_ms = ms_min; best = c; }
+      }
+      // restore state and bookkeeping: tuning is invisible
+      s->u = u0; s->v = v0; s->u_buf = ub0; s->v_buf = vb0;
+      s->parity = parity;
+      s->launches = launches;
+      cudaMemcpyAsync(s->u, su, bytes, cudaMemcpyDeviceToDevice, s->stream);
+      cudaMemcpyAsync(s->v, sv, bytes, cudaMemcpyDeviceToDevice, s->stream);
+      cudaStreamSynchronize(s->stream);
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
+    if (su) cudaFree(su);
+    if (sv) cudaFree(sv);
+    cudaGetLastError();
+  }
+  s->plan_variant = cands[best].variant;
+  s->plan_T = cands[best].T;
+  s->plan_iterations = iterations;
+  return SAYAL_OK;
+}
+
+int launch_projection_packed(Sim* s, int iterations, float d_t) {
+  if (s->ph.enable_pressure) return launch_projection_plain(s, iterations, d_t);  // pressure accumulates per cell: plain path
+  int r = packed_prepare(s, iterations);
+  if (r != SAYAL_OK) return r;
+  return run_passes(s, s->plan_variant, s->plan_T, iterations);
+}
+
+}  // namespace sayal

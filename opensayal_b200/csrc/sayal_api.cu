@@ -48,6 +48,7 @@ static void free_sim(Sim* s) {
   if (s->d_total_s) cudaFree(s->d_total_s);
   if (s->d_range) cudaFree(s->d_range);
   if (s->d_overflow) cudaFree(s->d_overflow);
+  if (s->d_timeline) cudaFree(s->d_timeline);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -123,9 +124,10 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   p.wt_pipe_height = c->wt_pipe_height;
   p.obstacle_radius = c->obstacle_radius;
 
-  s->projection_kernel = 1;
+  s->projection_kernel = 2;
   s->temporal_block = 0;  // 0 = auto
   s->use_graph = 1;
+  s->use_pdl = 1;
   s->autotune = 1;
   s->plan_variant = -1;
   s->force_variant = -1;
@@ -134,8 +136,9 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   if (const char* e = getenv("SAYAL_AUTOTUNE")) s->autotune = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_TEMPORAL_BLOCK")) { int t = atoi(e); if (t >= 0 && t <= tiled_max_temporal_block()) s->temporal_block = t; }
   if (const char* e = getenv("SAYAL_TILE_ROWS")) { int r = atoi(e); if (r == 8 || r == 10 || r == 12) s->force_variant = (r - 8) / 2; }
-  if (const char* e = getenv("SAYAL_PROJECTION_KERNEL")) s->projection_kernel = atoi(e) != 0;
+  if (const char* e = getenv("SAYAL_PROJECTION_KERNEL")) { int k = atoi(e); if (k >= 0 && k <= 2) s->projection_kernel = k; }
   if (const char* e = getenv("SAYAL_USE_GRAPH")) s->use_graph = atoi(e) != 0;
+  if (const char* e = getenv("SAYAL_USE_PDL")) s->use_pdl = atoi(e) != 0;
 
   auto fail = [&](int code) {
     free_sim(s);
@@ -175,6 +178,7 @@ static void swap_ptr(float*& a, float*& b) {
 
 static int projection(Sim* s, int iterations, float d_t) {
   if (iterations <= 0) return SAYAL_OK;
+  if (s->projection_kernel == 2) return launch_projection_packed(s, iterations, d_t);
   if (s->projection_kernel == 1) return launch_projection_tiled(s, iterations, d_t);
   return launch_projection_plain(s, iterations, d_t);
 }
@@ -260,7 +264,8 @@ int sayal_run(sayal_sim* sim, int32_t steps, float d_t) {
     invalidate_graphs(s);
     s->graph_dt = d_t;
   }
-  if (s->projection_kernel == 1) TRY(tiled_prepare(s, s->cfg.proj_n));  // timing is not capturable
+  if (s->projection_kernel == 2) TRY(packed_prepare(s, s->cfg.proj_n));  // timing is not capturable
+  if (s->projection_kernel == 1) TRY(tiled_prepare(s, s->cfg.proj_n));
   int remaining = steps;
   // One graph per starting parity holds ONE step; replaying it is followed by the same pointer swaps on
   // the host that capture performed, so the next replay (or eager call) sees the right front buffers.
@@ -463,8 +468,9 @@ int sayal_set_option(sayal_sim* sim, const char* key, int64_t value) {
   Sim* s = S(sim);
   invalidate_graphs(s);
   if (!strcmp(key, "projection_kernel")) {
-    if (value != 0 && value != 1) return set_error(SAYAL_EINVAL, "projection_kernel must be 0 or 1");
+    if (value < 0 || value > 2) return set_error(SAYAL_EINVAL, "projection_kernel must be 0, 1 or 2");
     s->projection_kernel = (int)value;
+    s->plan_variant = -1;
   } else if (!strcmp(key, "temporal_block")) {
     if (value < 0 || value > tiled_max_temporal_block()) return set_error(SAYAL_EINVAL, "temporal_block out of range");
     s->temporal_block = (int)value;
@@ -478,6 +484,16 @@ int sayal_set_option(sayal_sim* sim, const char* key, int64_t value) {
     s->plan_variant = -1;
   } else if (!strcmp(key, "use_graph")) {
     s->use_graph = value != 0;
+  } else if (!strcmp(key, "use_pdl")) {
+    s->use_pdl = value != 0;
+  } else if (!strcmp(key, "debug_timeline")) {  // profiling only: per-CTA phase timestamps (sayal_debug_timeline)
+    if (value && !s->d_timeline) {
+      s->timeline_cap = 5 * 65536;
+      CUDA_TRY(cudaMalloc(&s->d_timeline, s->timeline_cap * sizeof(long long)));
+    } else if (!value && s->d_timeline) {
+      cudaFree(s->d_timeline);
+      s->d_timeline = nullptr;
+    }
   } else {
     return set_error(SAYAL_EINVAL, "sayal_set_option: unknown key");
   }
@@ -490,6 +506,7 @@ int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value) {
   if (!strcmp(key, "projection_kernel")) *value = s->projection_kernel;
   else if (!strcmp(key, "temporal_block")) *value = s->temporal_block;
   else if (!strcmp(key, "use_graph")) *value = s->use_graph;
+  else if (!strcmp(key, "use_pdl")) *value = s->use_pdl;
   else if (!strcmp(key, "autotune")) *value = s->autotune;
   else if (!strcmp(key, "plan_temporal_block")) *value = s->plan_variant >= 0 ? s->plan_T : 0;
   else if (!strcmp(key, "plan_rows_per_warp")) *value = s->plan_variant >= 0 ? 8 + 2 * s->plan_variant : 0;
@@ -504,6 +521,19 @@ int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value) {
   else if (!strcmp(key, "own_lo")) *value = s->g.own_lo;
   else if (!strcmp(key, "own_hi")) *value = s->g.own_hi;
   else return set_error(SAYAL_EINVAL, "sayal_get_option: unknown key");
+  return SAYAL_OK;
+}
+
+int sayal_debug_timeline(sayal_sim* sim, int64_t* host_dst, int32_t max_tiles, int32_t* n_tiles) {
+  if (!sim || !host_dst || !n_tiles) return set_error(SAYAL_EINVAL, "sayal_debug_timeline: null argument");
+  Sim* s = S(sim);
+  *n_tiles = 0;
+  if (!s->d_timeline || s->timeline_tiles <= 0) return SAYAL_OK;
+  int n = s->timeline_tiles < max_tiles ? s->timeline_tiles : max_tiles;
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  CUDA_TRY(cudaMemcpy(host_dst, s->d_timeline, sizeof(long long) * 5 * (size_t)n, cudaMemcpyDeviceToHost));
+  *n_tiles = n;
   return SAYAL_OK;
 }
 

@@ -64,12 +64,16 @@ struct Sim {
   int32_t *d_is_solid, *d_total_s;  // built on demand for get_field / device_ptr
   int32_t* d_range;                 // ordered-int min / max of pressure
   int32_t* d_overflow;              // count of back-traces that left the local rows (slab runs)
+  long long* d_timeline;            // profiling only: per-CTA phase timestamps of the last projection pass
+  size_t timeline_cap;              // capacity in int64
+  int timeline_tiles;
   float min_p, max_p;
   bool range_valid;
   // options
-  int projection_kernel;  // 0 plain half-sweeps, 1 register tile
+  int projection_kernel;  // 0 plain half-sweeps, 1 register tile (scalar), 2 register tile (packed pairs + profile masks)
   int temporal_block;     // iterations per pass of the tiled kernel
   int use_graph;
+  int use_pdl;            // programmatic dependent launch between projection passes
   int fuse_forces;
   int autotune;           // time candidate tile plans on first use
   int force_variant;      // -1 = any tile variant
@@ -100,6 +104,11 @@ int launch_pack_rows(Sim* s, int local_row0, int nrows, int field_mask, float* d
 int launch_projection_tiled(Sim* s, int iterations, float d_t);
 int tiled_max_temporal_block();
 int tiled_prepare(Sim* s, int iterations);  // choose the tile plan (may time candidates; not capturable)
+
+// ---- projection_pack.cu ---------------------------------------------------------------------------
+int launch_projection_packed(Sim* s, int iterations, float d_t);
+int packed_max_temporal_block();
+int packed_prepare(Sim* s, int iterations);
 
 }  // namespace sayal
 

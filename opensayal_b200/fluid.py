@@ -274,6 +274,13 @@ class Fluid:
         check(self._lib.sayal_get_option(self._sim, key.encode(), C.byref(v)))
         return v.value
 
+    def debug_timeline(self, max_tiles: int = 65536) -> np.ndarray:
+        """Profiling only: (tiles, 5) int64 {entry, loaded, swept, stored (ns), SM id} of the last projection pass."""
+        out = np.zeros((max_tiles, 5), dtype=np.int64)
+        n = C.c_int32()
+        check(self._lib.sayal_debug_timeline(self._sim, out.ctypes.data_as(C.c_void_p), max_tiles, C.byref(n)))
+        return out[: n.value]
+
     @property
     def launch_count(self) -> int:
         return self._lib.sayal_launch_count(self._sim)

@@ -11,7 +11,7 @@ from opensayal_b200.synthetic import baseline_config, synthetic_fields
 pytestmark = pytest.mark.gpu
 
 
-def run_slabs(cfg, world, halo, steps, kernel=1):
+def run_slabs(cfg, world, halo, steps, kernel=2):
     c = cfg.c
     u, v, sm = synthetic_fields(c.width, c.height)
     slabs = []
@@ -35,7 +35,7 @@ def run_slabs(cfg, world, halo, steps, kernel=1):
     return out, overflow, ranges
 
 
-def run_single(cfg, steps, kernel=1):
+def run_single(cfg, steps, kernel=2):
     c = cfg.c
     f = Fluid(cfg)
     f.set_option("projection_kernel", kernel)
@@ -52,7 +52,7 @@ def run_single(cfg, steps, kernel=1):
 
 
 @pytest.mark.parametrize("world,halo", [(2, 16), (3, 12), (4, 32)])
-@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("kernel", [0, 1, 2])
 def test_slabs_bit_identical_to_single_gpu(world, halo, kernel):
     cfg = baseline_config(1, width=384, height=420)
     cfg["sim.projection.n"] = 20
