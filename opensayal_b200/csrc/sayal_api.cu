@@ -44,6 +44,7 @@ static void free_sim(Sim* s) {
   for (float* q : f)
     if (q) cudaFree(q);
   if (s->flags) cudaFree(s->flags);
+  if (s->geo) cudaFree(s->geo);
   if (s->d_is_solid) cudaFree(s->d_is_solid);
   if (s->d_total_s) cudaFree(s->d_total_s);
   if (s->d_range) cudaFree(s->d_range);
@@ -128,6 +129,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   s->temporal_block = 0;  // 0 = auto
   s->use_graph = 1;
   s->use_pdl = 1;
+  s->advect_kernel = 2;
   s->autotune = 1;
   s->plan_variant = -1;
   s->force_variant = -1;
@@ -138,6 +140,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   if (const char* e = getenv("SAYAL_TILE_ROWS")) { int r = atoi(e); if (r == 8 || r == 10 || r == 12) s->force_variant = (r - 8) / 2; }
   if (const char* e = getenv("SAYAL_PROJECTION_KERNEL")) { int k = atoi(e); if (k >= 0 && k <= 2) s->projection_kernel = k; }
   if (const char* e = getenv("SAYAL_USE_GRAPH")) s->use_graph = atoi(e) != 0;
+  if (const char* e = getenv("SAYAL_ADVECT_KERNEL")) { int k = atoi(e); if (k >= 0 && k <= 2) s->advect_kernel = k; }
   if (const char* e = getenv("SAYAL_USE_PDL")) s->use_pdl = atoi(e) != 0;
 
   auto fail = [&](int code) {
@@ -164,6 +167,10 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   cudaMemsetAsync(s->d_overflow, 0, sizeof(int32_t), s->stream);
   int r = launch_build_flags(s);
   if (r != SAYAL_OK) return fail(r);
+  e = cudaMalloc(&s->geo, field_elems(s) * sizeof(uint16_t));
+  if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
+  r = launch_build_geo(s);
+  if (r != SAYAL_OK) return fail(r);
   e = cudaStreamSynchronize(s->stream);
   if (e != cudaSuccess) return fail(set_error(SAYAL_ECUDA, cudaGetErrorString(e)));
   *out = s;
@@ -184,7 +191,8 @@ static int projection(Sim* s, int iterations, float d_t) {
 }
 
 static int advect_velocity(Sim* s, float d_t) {
-  TRY(launch_advect(s, d_t, true, false));
+  TRY(s->advect_kernel == 2 ? launch_advect_geo(s, d_t, true, false)
+      : s->advect_kernel == 1 ? launch_advect_tile(s, d_t, true, false) : launch_advect(s, d_t, true, false));
   swap_ptr(s->u, s->u_buf);  // update_velocity_advection_at (fluid.cu:614-617) as a pointer swap
   swap_ptr(s->v, s->v_buf);
   s->parity ^= 1;
@@ -192,7 +200,8 @@ static int advect_velocity(Sim* s, float d_t) {
 }
 
 static int advect_smoke(Sim* s, float d_t) {
-  TRY(launch_advect(s, d_t, false, true));
+  TRY(s->advect_kernel == 2 ? launch_advect_geo(s, d_t, false, true)
+      : s->advect_kernel == 1 ? launch_advect_tile(s, d_t, false, true) : launch_advect(s, d_t, false, true));
   swap_ptr(s->smoke, s->smoke_buf);  // update_smoke_advection_at (fluid.cu:569-571)
   s->parity ^= 2;
   return SAYAL_OK;
@@ -484,6 +493,9 @@ int sayal_set_option(sayal_sim* sim, const char* key, int64_t value) {
     s->plan_variant = -1;
   } else if (!strcmp(key, "use_graph")) {
     s->use_graph = value != 0;
+  } else if (!strcmp(key, "advect_kernel")) {
+    if (value < 0 || value > 2) return set_error(SAYAL_EINVAL, "advect_kernel must be 0, 1 or 2");
+    s->advect_kernel = (int)value;
   } else if (!strcmp(key, "use_pdl")) {
     s->use_pdl = value != 0;
   } else if (!strcmp(key, "debug_timeline")) {  // profiling only: per-CTA phase timestamps (sayal_debug_timeline)
@@ -507,6 +519,7 @@ int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value) {
   else if (!strcmp(key, "temporal_block")) *value = s->temporal_block;
   else if (!strcmp(key, "use_graph")) *value = s->use_graph;
   else if (!strcmp(key, "use_pdl")) *value = s->use_pdl;
+  else if (!strcmp(key, "advect_kernel")) *value = s->advect_kernel;
   else if (!strcmp(key, "autotune")) *value = s->autotune;
   else if (!strcmp(key, "plan_temporal_block")) *value = s->plan_variant >= 0 ? s->plan_T : 0;
   else if (!strcmp(key, "plan_rows_per_warp")) *value = s->plan_variant >= 0 ? 8 + 2 * s->plan_variant : 0;

@@ -61,6 +61,7 @@ struct Sim {
   // fp32 fields, local_rows x pitch
   float *u, *v, *p, *smoke, *u_buf, *v_buf, *smoke_buf;
   uint8_t* flags;
+  uint16_t* geo;                    // static per-cell geometry word of the tile advection (advect_tile.cu)
   int32_t *d_is_solid, *d_total_s;  // built on demand for get_field / device_ptr
   int32_t* d_range;                 // ordered-int min / max of pressure
   int32_t* d_overflow;              // count of back-traces that left the local rows (slab runs)
@@ -73,6 +74,7 @@ struct Sim {
   int projection_kernel;  // 0 plain half-sweeps, 1 register tile (scalar), 2 register tile (packed pairs + profile masks)
   int temporal_block;     // iterations per pass of the tiled kernel
   int use_graph;
+  int advect_kernel;      // 0 plain per-cell kernels, 1 shared-memory tiles, 2 direct with geometry words (cell_size 1)
   int use_pdl;            // programmatic dependent launch between projection passes
   int fuse_forces;
   int autotune;           // time candidate tile plans on first use
@@ -99,6 +101,11 @@ int launch_extrapolation(Sim* s);
 int launch_advect(Sim* s, float d_t, bool velocity, bool smoke);
 int launch_sample_velocity(Sim* s, int n, const float* d_xs, const float* d_ys, float* d_ou, float* d_ov);
 int launch_pack_rows(Sim* s, int local_row0, int nrows, int field_mask, float* dev_buf, bool unpack);
+
+// ---- advect_tile.cu -------------------------------------------------------------------------------
+int launch_build_geo(Sim* s);
+int launch_advect_tile(Sim* s, float d_t, bool velocity, bool smoke);
+int launch_advect_geo(Sim* s, float d_t, bool velocity, bool smoke);
 
 // ---- projection_tile.cu --------------------------------------------------------------------------
 int launch_projection_tiled(Sim* s, int iterations, float d_t);

@@ -128,11 +128,14 @@ def test_extrapolation_bit_exact():
 
 
 @pytest.mark.parametrize("name", list(CONFIGS))
-def test_advection_bit_exact(name):
+@pytest.mark.parametrize("kernel", [0, 1, 2])
+def test_advection_bit_exact(name, kernel):
+    """kernel 0 = plain per-cell kernels, 1 = shared-memory tile kernels, 2 = direct geometry-word kernels."""
     cfg = CONFIGS[name]()
     cfg["sim.smoke.enable_decay"] = 1
     cfg["sim.smoke.decay_rate"] = 0.3
     gpu, cpu = pair(cfg)
+    gpu.set_option("advect_kernel", kernel)
     gpu.stage_advect_velocity(0.05)
     cpu.advect_velocity(0.05)
     assert_same(gpu, cpu, names=("u", "v"), what="velocity advection")
@@ -141,10 +144,14 @@ def test_advection_bit_exact(name):
     assert_same(gpu, cpu, names=("smoke",), what="smoke advection + decay")
 
 
-def test_advection_fast_flow_far_backtrace():
-    """Wind-tunnel speeds: back-traces of 10+ cells, leaving the domain on the left (fluid.cu:422-424)."""
+@pytest.mark.parametrize("kernel", [0, 1, 2])
+@pytest.mark.parametrize("amplitude", [150.0, 400.0, 3000.0])
+def test_advection_fast_flow_far_backtrace(kernel, amplitude):
+    """Wind-tunnel speeds and beyond: back-traces of 7 / 20 / 150 cells — inside the staged window, beyond it
+    (global fallback of the tile kernels), and leaving the domain (fluid.cu:422-424)."""
     cfg = baseline_config(1, width=384, height=216)
-    gpu, cpu = pair(cfg, amplitude=400.0)
+    gpu, cpu = pair(cfg, amplitude=amplitude)
+    gpu.set_option("advect_kernel", kernel)
     gpu.stage_advect_velocity(0.05)
     cpu.advect_velocity(0.05)
     gpu.stage_advect_smoke(0.05)
@@ -267,6 +274,25 @@ def test_full_size_1920x1080_one_step_and_properties():
     gpu.update(None)
     cpu.step(None)
     assert_same(gpu, cpu, what="1920x1080 step")
+
+
+def test_tile_advection_equals_plain_at_full_size():
+    """Size-independent property at BASELINE sizes: the tile kernels and the plain kernels agree bit for bit
+    (1920x1080 wind tunnel after two steps, so the inlet jet and the wake are in the field)."""
+    cfg = baseline_config(1)
+    u, v, sm = synthetic_fields(1920, 1080)
+    outs = []
+    for kernel in (0, 1, 2):
+        f = Fluid(cfg)
+        f.set_option("advect_kernel", kernel)
+        for name, a in (("u", u), ("v", v), ("smoke", sm)):
+            f.set_field(name, a)
+        f.run(2)
+        outs.append([f.get_field(n) for n in ("u", "v", "smoke")])
+        f.close()
+    for other in outs[1:]:
+        for a, b, n in zip(outs[0], other, ("u", "v", "smoke")):
+            assert np.array_equal(a, b), n
 
 
 def test_large_grid_properties_3840x2160():
