@@ -164,7 +164,8 @@ int sayal_stage_advect_smoke(sayal_sim* sim, float d_t);
 /* Tuning / introspection.  set: "projection_kernel" (0 = plain half-sweeps, 1 = register-tile temporally
  * blocked), "temporal_block" (iterations per pass, 0 = choose), "tile_rows_per_warp" (0 = choose, 8/10/12),
  * "autotune" (time candidate tile plans on first use), "use_graph".  get: the same plus "plan_temporal_block",
- * "plan_rows_per_warp", "halo_overflow", "pitch", "local_rows", "own_lo", "own_hi".  No option changes results. */
+ * "plan_rows_per_warp", "halo_overflow", "link_error", "pitch", "local_rows", "own_lo", "own_hi".  No option
+ * changes results. */
 int sayal_set_option(sayal_sim* sim, const char* key, int64_t value);
 int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value);
 /* Profiling only (option "debug_timeline" = 1): per-CTA timestamps of the last projection pass, 5 int64 per tile
@@ -182,6 +183,20 @@ void* sayal_stream(sayal_sim* sim);
 int sayal_slab_pack_edge(sayal_sim* sim, int32_t side, int32_t nrows, int32_t field_mask, void* dev_buf);
 int sayal_slab_unpack_ghost(sayal_sim* sim, int32_t side, int32_t nrows, int32_t field_mask,
                             const void* dev_buf);
+
+/* ---- slab links: ghost rows over NVLink peer memory, no host in the loop (slab_exchange.cu) ----------------
+ * Each slab sim owns one neighbour-writable device block.  Processes trade its CUDA IPC handle once
+ * (export on the owner, connect on the neighbour; `side` 0 = the neighbour holding the rows above mine in memory,
+ * 1 = below); slabs living in one process connect directly.  Once a slab has a neighbour, sayal_step / sayal_run
+ * run the whole slab schedule — projection in chunks of halo/2 iterations with an exchange of u, v after each,
+ * exchanges after velocity and smoke advection — on the sim's stream, graph-captured by sayal_run.  The ranks
+ * must issue the same sequence of steps. */
+#define SAYAL_IPC_HANDLE_BYTES 64
+int sayal_slab_ipc_export(sayal_sim* sim, void* handle_out /* 64 bytes */, int64_t* stage_elems);
+int sayal_slab_ipc_connect(sayal_sim* sim, int32_t side, const void* handle /* 64 bytes */, int64_t stage_elems);
+int sayal_slab_connect_local(sayal_sim* sim, int32_t side, sayal_sim* neighbour);
+/* One exchange of the `halo` edge rows of the fields in field_mask (1 = U, 2 = V, 4 = SMOKE) with both neighbours. */
+int sayal_slab_exchange(sayal_sim* sim, int32_t field_mask);
 
 const char* sayal_last_error(void);
 int sayal_abi_version(void);

@@ -116,6 +116,10 @@ SYMBOLS = [
     ("sayal_stream", C.c_void_p, [_simp]),
     ("sayal_slab_pack_edge", C.c_int, [_simp, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     ("sayal_slab_unpack_ghost", C.c_int, [_simp, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    ("sayal_slab_ipc_export", C.c_int, [_simp, C.c_void_p, C.POINTER(C.c_int64)]),
+    ("sayal_slab_ipc_connect", C.c_int, [_simp, C.c_int32, C.c_void_p, C.c_int64]),
+    ("sayal_slab_connect_local", C.c_int, [_simp, C.c_int32, _simp]),
+    ("sayal_slab_exchange", C.c_int, [_simp, C.c_int32]),
     ("sayal_last_error", C.c_char_p, []),
     ("sayal_abi_version", C.c_int, []),
 ]

@@ -490,14 +490,19 @@ int run_passes(Sim* s, int variant, int T, int iterations) {
 
 }  // namespace
 
-int packed_max_temporal_block() { return kMaxT; }
+int tiled_max_temporal_block() { return kMaxT; }
 
 // Choose (tile variant, temporal block) for `iterations` SOR iterations on this grid: rank all candidates
 // with the wave-quantisation model, then time the best few on the live arrays (state saved and restored;
 // every candidate produces the same bits, so the choice never changes results).
-int packed_prepare(Sim* s, int iterations) {
+int tiled_prepare(Sim* s, int iterations) {
   if (s->ph.enable_pressure || iterations <= 0) return SAYAL_OK;
-  if (s->plan_iterations == iterations && s->plan_variant >= 0) return SAYAL_OK;
+  for (int k = 0; k < s->n_plans; k++)
+    if (s->plans[k].iterations == iterations) {  // slab runs alternate between chunk sizes: keep every plan
+      s->plan_variant = s->plans[k].variant;
+      s->plan_T = s->plans[k].T;
+      return SAYAL_OK;
+    }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
   struct Cand { int variant, T; double cost; float ms; };
@@ -561,13 +566,14 @@ int packed_prepare(Sim* s, int iterations) {
   }
   s->plan_variant = cands[best].variant;
   s->plan_T = cands[best].T;
-  s->plan_iterations = iterations;
+  if (s->n_plans == Sim::kMaxPlans) s->n_plans = 0;  // full: start over (never happens with <= 8 chunk sizes)
+  s->plans[s->n_plans++] = {iterations, s->plan_variant, s->plan_T};
   return SAYAL_OK;
 }
 
-int launch_projection_packed(Sim* s, int iterations, float d_t) {
+int launch_projection_tiled(Sim* s, int iterations, float d_t) {
   if (s->ph.enable_pressure) return launch_projection_plain(s, iterations, d_t);  // pressure accumulates per cell: plain path
-  int r = packed_prepare(s, iterations);
+  int r = tiled_prepare(s, iterations);
   if (r != SAYAL_OK) return r;
   return run_passes(s, s->plan_variant, s->plan_T, iterations);
 }

@@ -50,6 +50,10 @@ static void free_sim(Sim* s) {
   if (s->d_range) cudaFree(s->d_range);
   if (s->d_overflow) cudaFree(s->d_overflow);
   if (s->d_timeline) cudaFree(s->d_timeline);
+  for (int k = 0; k < 2; k++)
+    if (s->ipc_opened[k]) cudaIpcCloseMemHandle(s->ipc_opened[k]);
+  if (s->link_block) cudaFree(s->link_block);
+  if (s->link_counters) cudaFree(s->link_counters);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -96,6 +100,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
     g.local_rows = hi - lo;
     g.own_lo = slab->row0 - lo;
     g.own_hi = g.own_lo + slab->rows;
+    s->slab_halo = slab->halo;
   } else {
     g.row_base = 0;
     g.local_rows = c->height;
@@ -125,20 +130,20 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   p.wt_pipe_height = c->wt_pipe_height;
   p.obstacle_radius = c->obstacle_radius;
 
-  s->projection_kernel = 2;
+  s->projection_kernel = 1;
   s->temporal_block = 0;  // 0 = auto
   s->use_graph = 1;
   s->use_pdl = 1;
   s->advect_kernel = 2;
   s->autotune = 1;
-  s->plan_variant = -1;
+  s->plan_variant = -1, s->n_plans = 0;
   s->force_variant = -1;
   // experiment / profiling overrides (never change results): SAYAL_AUTOTUNE=0, SAYAL_TEMPORAL_BLOCK=T,
   // SAYAL_TILE_ROWS=8|10|12, SAYAL_PROJECTION_KERNEL=0|1, SAYAL_USE_GRAPH=0|1
   if (const char* e = getenv("SAYAL_AUTOTUNE")) s->autotune = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_TEMPORAL_BLOCK")) { int t = atoi(e); if (t >= 0 && t <= tiled_max_temporal_block()) s->temporal_block = t; }
   if (const char* e = getenv("SAYAL_TILE_ROWS")) { int r = atoi(e); if (r == 8 || r == 10 || r == 12) s->force_variant = (r - 8) / 2; }
-  if (const char* e = getenv("SAYAL_PROJECTION_KERNEL")) { int k = atoi(e); if (k >= 0 && k <= 2) s->projection_kernel = k; }
+  if (const char* e = getenv("SAYAL_PROJECTION_KERNEL")) s->projection_kernel = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_USE_GRAPH")) s->use_graph = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_ADVECT_KERNEL")) { int k = atoi(e); if (k >= 0 && k <= 2) s->advect_kernel = k; }
   if (const char* e = getenv("SAYAL_USE_PDL")) s->use_pdl = atoi(e) != 0;
@@ -185,7 +190,6 @@ static void swap_ptr(float*& a, float*& b) {
 
 static int projection(Sim* s, int iterations, float d_t) {
   if (iterations <= 0) return SAYAL_OK;
-  if (s->projection_kernel == 2) return launch_projection_packed(s, iterations, d_t);
   if (s->projection_kernel == 1) return launch_projection_tiled(s, iterations, d_t);
   return launch_projection_plain(s, iterations, d_t);
 }
@@ -208,22 +212,41 @@ static int advect_smoke(Sim* s, float d_t) {
 }
 
 // Fluid::update (fluid.cu:770-795)
+bool is_linked(const Sim* s);
+
 static int step_impl(Sim* s, const sayal_source* src, float d_t) {
+  const bool linked = is_linked(s);
   TRY(launch_forces(s, src, d_t));
   if (s->ph.enable_pressure) TRY(launch_zero_pressure(s));
   // viscosity: the reference's racy diffusion loop (fluid.cu:185-190, H1) is out of scope; see DESIGN.md
-  TRY(projection(s, s->cfg.proj_n, d_t));
+  if (!linked) {
+    TRY(projection(s, s->cfg.proj_n, d_t));
+  } else {
+    // y-slab: `halo` ghost rows keep the owned rows exact for halo/2 iterations, then neighbours swap edge rows
+    const int per = s->slab_halo / 2;
+    for (int done = 0; done < s->cfg.proj_n;) {
+      int k = s->cfg.proj_n - done < per ? s->cfg.proj_n - done : per;
+      TRY(projection(s, k, d_t));
+      TRY(launch_slab_exchange(s, 1 | 2));
+      done += k;
+    }
+  }
   if (s->ph.enable_pressure) {
     TRY(launch_pressure_range(s));
     s->range_valid = false;
   }
   TRY(launch_extrapolation(s));
   TRY(advect_velocity(s, d_t));
-  if (s->ph.enable_smoke && s->ph.wt_smoke != 0.f) TRY(advect_smoke(s, d_t));  // decay fused (fluid.cu:792)
+  if (linked) TRY(launch_slab_exchange(s, 1 | 2));
+  if (s->ph.enable_smoke && s->ph.wt_smoke != 0.f) {
+    TRY(advect_smoke(s, d_t));  // decay fused (fluid.cu:792)
+    if (linked) TRY(launch_slab_exchange(s, 4));
+  }
   return SAYAL_OK;
 }
 
 static bool is_slab(const Sim* s) { return s->g.local_rows != s->g.H; }
+bool is_linked(const Sim* s) { return s->link_block && (s->link.peer_recv[0] || s->link.peer_recv[1]); }
 
 }  // namespace sayal
 
@@ -258,7 +281,8 @@ void sayal_destroy(sayal_sim* sim) { free_sim(S(sim)); }
 int sayal_step(sayal_sim* sim, const sayal_source* src, float d_t) {
   if (!sim) return set_error(SAYAL_EINVAL, "sayal_step: null sim");
   Sim* s = S(sim);
-  if (is_slab(s)) return set_error(SAYAL_EINVAL, "sayal_step: slab sims are stepped stage by stage with ghost exchange (see opensayal_b200/slab.py)");
+  if (is_slab(s) && !is_linked(s)) return set_error(SAYAL_EINVAL, "sayal_step: a slab sim must be linked to its neighbours first (sayal_slab_ipc_connect / sayal_slab_connect_local), or stepped stage by stage");
+  if (is_linked(s) && s->slab_halo < 2) return set_error(SAYAL_EINVAL, "sayal_step: linked slabs need halo >= 2");
   CUDA_TRY(cudaSetDevice(s->device));
   return step_impl(s, src, d_t);
 }
@@ -266,15 +290,23 @@ int sayal_step(sayal_sim* sim, const sayal_source* src, float d_t) {
 int sayal_run(sayal_sim* sim, int32_t steps, float d_t) {
   if (!sim) return set_error(SAYAL_EINVAL, "sayal_run: null sim");
   Sim* s = S(sim);
-  if (is_slab(s)) return set_error(SAYAL_EINVAL, "sayal_run: slab sims are stepped stage by stage with ghost exchange");
+  if (is_slab(s) && !is_linked(s)) return set_error(SAYAL_EINVAL, "sayal_run: a slab sim must be linked to its neighbours first");
+  if (is_linked(s) && s->slab_halo < 2) return set_error(SAYAL_EINVAL, "sayal_run: linked slabs need halo >= 2");
   if (steps < 0) return set_error(SAYAL_EINVAL, "sayal_run: steps < 0");
   CUDA_TRY(cudaSetDevice(s->device));
   if (s->graph_dt != d_t) {
     invalidate_graphs(s);
     s->graph_dt = d_t;
   }
-  if (s->projection_kernel == 2) TRY(packed_prepare(s, s->cfg.proj_n));  // timing is not capturable
-  if (s->projection_kernel == 1) TRY(tiled_prepare(s, s->cfg.proj_n));
+  if (s->projection_kernel == 1) {  // timing is not capturable: choose every plan the step will use first
+    if (!is_linked(s)) {
+      TRY(tiled_prepare(s, s->cfg.proj_n));
+    } else {
+      const int per = s->slab_halo / 2;
+      if (s->cfg.proj_n >= per) TRY(tiled_prepare(s, per));
+      if (s->cfg.proj_n % per) TRY(tiled_prepare(s, s->cfg.proj_n % per));
+    }
+  }
   int remaining = steps;
   // One graph per starting parity holds ONE step; replaying it is followed by the same pointer swaps on
   // the host that capture performed, so the next replay (or eager call) sees the right front buffers.
@@ -477,20 +509,20 @@ int sayal_set_option(sayal_sim* sim, const char* key, int64_t value) {
   Sim* s = S(sim);
   invalidate_graphs(s);
   if (!strcmp(key, "projection_kernel")) {
-    if (value < 0 || value > 2) return set_error(SAYAL_EINVAL, "projection_kernel must be 0, 1 or 2");
+    if (value < 0 || value > 1) return set_error(SAYAL_EINVAL, "projection_kernel must be 0 or 1");
     s->projection_kernel = (int)value;
-    s->plan_variant = -1;
+    s->plan_variant = -1, s->n_plans = 0;
   } else if (!strcmp(key, "temporal_block")) {
     if (value < 0 || value > tiled_max_temporal_block()) return set_error(SAYAL_EINVAL, "temporal_block out of range");
     s->temporal_block = (int)value;
-    s->plan_variant = -1;
+    s->plan_variant = -1, s->n_plans = 0;
   } else if (!strcmp(key, "tile_rows_per_warp")) {  // 0 = any, else 8 / 10 / 12
     if (value != 0 && value != 8 && value != 10 && value != 12) return set_error(SAYAL_EINVAL, "tile_rows_per_warp must be 0, 8, 10 or 12");
     s->force_variant = value == 0 ? -1 : (int)(value - 8) / 2;
-    s->plan_variant = -1;
+    s->plan_variant = -1, s->n_plans = 0;
   } else if (!strcmp(key, "autotune")) {
     s->autotune = value != 0;
-    s->plan_variant = -1;
+    s->plan_variant = -1, s->n_plans = 0;
   } else if (!strcmp(key, "use_graph")) {
     s->use_graph = value != 0;
   } else if (!strcmp(key, "advect_kernel")) {
@@ -529,6 +561,14 @@ int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value) {
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     CUDA_TRY(cudaMemcpy(&v, s->d_overflow, sizeof v, cudaMemcpyDeviceToHost));
     *value = v;
+  } else if (!strcmp(key, "link_error")) {
+    int32_t v = 0;
+    if (s->link_block) {
+      CUDA_TRY(cudaSetDevice(s->device));
+      CUDA_TRY(cudaStreamSynchronize(s->stream));
+      CUDA_TRY(cudaMemcpy(&v, s->link.link_error, sizeof v, cudaMemcpyDeviceToHost));
+    }
+    *value = v;
   } else if (!strcmp(key, "pitch")) *value = s->g.pitch;
   else if (!strcmp(key, "local_rows")) *value = s->g.local_rows;
   else if (!strcmp(key, "own_lo")) *value = s->g.own_lo;
@@ -552,6 +592,61 @@ int sayal_debug_timeline(sayal_sim* sim, int64_t* host_dst, int32_t max_tiles, i
 
 int64_t sayal_launch_count(sayal_sim* sim) { return sim ? S(sim)->launches : 0; }
 void* sayal_stream(sayal_sim* sim) { return sim ? (void*)S(sim)->stream : nullptr; }
+
+// ---- slab links ---------------------------------------------------------------------------------------
+int sayal_slab_ipc_export(sayal_sim* sim, void* handle_out, int64_t* stage_elems) {
+  STAGE_PROLOGUE("sayal_slab_ipc_export");
+  if (!handle_out || !stage_elems) return set_error(SAYAL_EINVAL, "sayal_slab_ipc_export: null argument");
+  TRY(slab_link_alloc(s));
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, s->link_block));
+  static_assert(sizeof(h) == SAYAL_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(handle_out, &h, sizeof h);
+  *stage_elems = (int64_t)slab_link_stage_elems(s);
+  return SAYAL_OK;
+}
+
+int sayal_slab_ipc_connect(sayal_sim* sim, int32_t side, const void* handle, int64_t stage_elems) {
+  STAGE_PROLOGUE("sayal_slab_ipc_connect");
+  if (!handle || (side != 0 && side != 1)) return set_error(SAYAL_EINVAL, "sayal_slab_ipc_connect: bad argument");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof h);
+  void* p = nullptr;
+  CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  int r = slab_link_connect(s, side, p, (size_t)stage_elems);
+  if (r != SAYAL_OK) {
+    cudaIpcCloseMemHandle(p);
+    return r;
+  }
+  s->ipc_opened[side] = p;
+  invalidate_graphs(s);
+  return SAYAL_OK;
+}
+
+int sayal_slab_connect_local(sayal_sim* sim, int32_t side, sayal_sim* neighbour) {
+  STAGE_PROLOGUE("sayal_slab_connect_local");
+  if (!neighbour) return set_error(SAYAL_EINVAL, "sayal_slab_connect_local: null neighbour");
+  Sim* n = S(neighbour);
+  CUDA_TRY(cudaSetDevice(n->device));
+  TRY(slab_link_alloc(n));
+  CUDA_TRY(cudaSetDevice(s->device));
+  if (n->device != s->device) {
+    int can = 0;
+    CUDA_TRY(cudaDeviceCanAccessPeer(&can, s->device, n->device));
+    if (!can) return set_error(SAYAL_EINVAL, "sayal_slab_connect_local: no peer access between the two devices");
+    cudaError_t e = cudaDeviceEnablePeerAccess(n->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return set_error(SAYAL_ECUDA, cudaGetErrorString(e));
+    cudaGetLastError();
+  }
+  TRY(slab_link_connect(s, side, n->link_block, slab_link_stage_elems(n)));
+  invalidate_graphs(s);
+  return SAYAL_OK;
+}
+
+int sayal_slab_exchange(sayal_sim* sim, int32_t field_mask) {
+  STAGE_PROLOGUE("sayal_slab_exchange");
+  return launch_slab_exchange(s, field_mask);
+}
 
 // ---- slab edge rows ---------------------------------------------------------------------------------
 // side 0 = low memory rows (towards r = 0), side 1 = high memory rows.

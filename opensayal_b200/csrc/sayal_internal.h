@@ -52,6 +52,17 @@ struct Phys {
   float obstacle_radius;
 };
 
+// Device-side view of a slab's links to its two neighbours (slab_exchange.cu); side 0 = low memory rows.
+struct SlabLinkDev {
+  float* peer_recv[2];    // where my edge rows land in the neighbour's block (null: no neighbour on that side)
+  unsigned* peer_flag[2]; // the neighbour's flag word for my pushes
+  float* my_recv[2];      // where the neighbours' rows land here (2 parities each)
+  unsigned* my_flag;      // [2], written by the neighbours
+  unsigned *send_seq, *recv_seq, *ticket;  // private counters, advanced by the kernels
+  int* link_error;        // raised when a wait gave up
+  size_t stage_elems;     // floats per receive buffer: halo * W * 3
+};
+
 struct Sim {
   sayal_config cfg;
   Grid g;
@@ -71,7 +82,7 @@ struct Sim {
   float min_p, max_p;
   bool range_valid;
   // options
-  int projection_kernel;  // 0 plain half-sweeps, 1 register tile (scalar), 2 register tile (packed pairs + profile masks)
+  int projection_kernel;  // 0 plain half-sweeps, 1 register tile (packed pairs + profile multipliers)
   int temporal_block;     // iterations per pass of the tiled kernel
   int use_graph;
   int advect_kernel;      // 0 plain per-cell kernels, 1 shared-memory tiles, 2 direct with geometry words (cell_size 1)
@@ -79,7 +90,10 @@ struct Sim {
   int fuse_forces;
   int autotune;           // time candidate tile plans on first use
   int force_variant;      // -1 = any tile variant
-  int plan_variant, plan_T, plan_iterations;  // chosen tile plan (projection_tile.cu)
+  int plan_variant, plan_T;  // tile plan of the last projection (projection_pack.cu)
+  static constexpr int kMaxPlans = 8;
+  struct Plan { int iterations, variant, T; } plans[kMaxPlans];  // one per iteration count seen
+  int n_plans;
   // CUDA graph cache for sayal_run: one single-step graph per starting buffer parity, with the
   // pointer assignment the step leaves behind (the step swaps front and back buffers)
   cudaGraphExec_t graph[4];   // indexed by `parity`
@@ -88,6 +102,12 @@ struct Sim {
   float graph_dt;
   int parity;  // bit 0: (u,v) and their back buffers are swapped; bit 1: smoke and its back buffer are
   int64_t launches;
+  // y-slab links (slab_exchange.cu)
+  int slab_halo;            // ghost rows per interior side as requested at creation (0: whole domain)
+  void* link_block;         // neighbour-writable block (flags + receive areas), IPC-exportable
+  unsigned* link_counters;  // private
+  SlabLinkDev link;
+  void* ipc_opened[2];      // peer blocks opened with cudaIpcOpenMemHandle (closed on destroy)
 };
 
 // ---- kernels_basic.cu ---------------------------------------------------------------------------
@@ -107,15 +127,17 @@ int launch_build_geo(Sim* s);
 int launch_advect_tile(Sim* s, float d_t, bool velocity, bool smoke);
 int launch_advect_geo(Sim* s, float d_t, bool velocity, bool smoke);
 
-// ---- projection_tile.cu --------------------------------------------------------------------------
+// ---- slab_exchange.cu -----------------------------------------------------------------------------
+int slab_link_alloc(Sim* s);
+int slab_link_connect(Sim* s, int side, void* peer_block, size_t peer_stage_elems);
+size_t slab_link_stage_elems(const Sim* s);
+int launch_slab_exchange(Sim* s, int field_mask);
+
+// ---- projection_pack.cu --------------------------------------------------------------------------
 int launch_projection_tiled(Sim* s, int iterations, float d_t);
 int tiled_max_temporal_block();
 int tiled_prepare(Sim* s, int iterations);  // choose the tile plan (may time candidates; not capturable)
 
-// ---- projection_pack.cu ---------------------------------------------------------------------------
-int launch_projection_packed(Sim* s, int iterations, float d_t);
-int packed_max_temporal_block();
-int packed_prepare(Sim* s, int iterations);
 
 }  // namespace sayal
 

@@ -289,6 +289,22 @@ class Fluid:
     def stream(self) -> int:
         return self._lib.sayal_stream(self._sim) or 0
 
+    # slab links (NVLink peer memory; see slab.py and csrc/slab_exchange.cu)
+    def ipc_export(self) -> Tuple[bytes, int]:
+        buf = C.create_string_buffer(64)
+        n = C.c_int64()
+        check(self._lib.sayal_slab_ipc_export(self._sim, buf, C.byref(n)))
+        return buf.raw, n.value
+
+    def ipc_connect(self, side: int, handle: bytes, stage_elems: int) -> None:
+        check(self._lib.sayal_slab_ipc_connect(self._sim, side, C.c_char_p(handle), stage_elems))
+
+    def connect_local(self, side: int, neighbour: "Fluid") -> None:
+        check(self._lib.sayal_slab_connect_local(self._sim, side, neighbour._sim))
+
+    def slab_exchange(self, field_mask: int) -> None:
+        check(self._lib.sayal_slab_exchange(self._sim, field_mask))
+
     # slab plumbing (see slab.py)
     def pack_edge(self, side: int, nrows: int, field_mask: int, dev_ptr: int):
         check(self._lib.sayal_slab_pack_edge(self._sim, side, nrows, field_mask, C.c_void_p(dev_ptr)))

@@ -191,11 +191,37 @@ def run_schedule_dist(slab, ops: Sequence[tuple], rank: int, world: int, source=
             slab.apply(op, source, d_t)
 
 
-class SlabFluid:
-    """`Fluid` over N y-slabs, one process per slab (torch.distributed must be initialised)."""
+def link_local(slabs: Sequence) -> None:
+    """Connect slabs that live in ONE process (same or peer-accessible devices) for the native exchange."""
+    sims = [getattr(s, "sim", s) for s in slabs]
+    for a, b in zip(sims[:-1], sims[1:]):  # a holds the rows above b
+        a.connect_local(1, b)
+        b.connect_local(0, a)
 
-    def __init__(self, cfg, rank: int, world: int, device: int, halo: int = 16, group=None):
+
+def link_dist(sim, rank: int, world: int, group=None) -> None:
+    """Trade CUDA IPC handles of the neighbour-writable blocks with the two neighbour ranks (once)."""
+    import torch.distributed as dist
+    mine = sim.ipc_export()
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine, group=group)
+    if rank > 0:
+        sim.ipc_connect(0, *everyone[rank - 1])
+    if rank < world - 1:
+        sim.ipc_connect(1, *everyone[rank + 1])
+    dist.barrier(group=group)
+
+
+class SlabFluid:
+    """`Fluid` over N y-slabs, one process per slab (torch.distributed must be initialised).
+
+    transport "p2p" (default): ghost rows travel as peer-memory stores over NVLink issued by the library's own
+    kernels on the sim's stream (csrc/slab_exchange.cu) and the whole step is one CUDA-graph replay per rank.
+    transport "nccl": the same schedule driven from here, edge rows packed and sent with NCCL send/recv."""
+
+    def __init__(self, cfg, rank: int, world: int, device: int, halo: int = 16, group=None, transport: str = "p2p"):
         self.cfg, self.rank, self.world, self.group = cfg, rank, world, group
+        self.transport = transport if world > 1 else "none"
         c = cfg.c
         row0, rows = slab_rows(c.height, world, rank)
         if world > 1 and rows < halo:
@@ -204,6 +230,9 @@ class SlabFluid:
         self.slab = FluidSlab(cfg, device, row0, rows, halo if world > 1 else 0, rank == 0, rank == world - 1)
         self.ops = step_schedule(c.proj_n, halo, bool(c.enable_pressure), bool(c.enable_smoke) and c.wt_smoke != 0) \
             if world > 1 else None
+        if self.transport == "p2p":
+            link_dist(self.sim, rank, world, group)
+            self.sim.run(0)  # choose the projection tile plans (may time candidates) before the first exchange
 
     @property
     def sim(self):
@@ -214,14 +243,24 @@ class SlabFluid:
         self.sim.set_field("u", u)
         self.sim.set_field("v", v)
         self.sim.set_field("smoke", smoke)
-        if self.world > 1:
+        if self.transport == "p2p":
+            self.sim.slab_exchange(F_U | F_V | F_SMOKE)
+        elif self.world > 1:
             exchange_dist(self.slab, F_U | F_V | F_SMOKE, self.rank, self.world, self.group)
 
     def update(self, source=None, d_t=None) -> None:
-        if self.world == 1:
+        if self.transport in ("none", "p2p"):
             self.sim.step_async(source, d_t)
         else:
             run_schedule_dist(self.slab, self.ops, self.rank, self.world, source, d_t, self.group)
+
+    def run(self, steps: int, d_t=None) -> None:
+        """`steps` updates with an inactive source; one graph replay per step on the native transports."""
+        if self.transport in ("none", "p2p"):
+            self.sim.run(steps, d_t)
+        else:
+            for _ in range(steps):
+                self.update(None, d_t)
 
     def sync(self) -> None:
         self.sim.sync()
@@ -265,14 +304,14 @@ def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSa
     cfg = workload_config(world)
     c = cfg.c
     halo = int(os.environ.get("SAYAL_SLAB_HALO", "32"))
-    sf = SlabFluid(cfg, rank, world, local, halo=halo)
+    transport = os.environ.get("SAYAL_SLAB_TRANSPORT", "p2p")
+    sf = SlabFluid(cfg, rank, world, local, halo=halo, transport=transport)
     u, v, sm = synthetic_fields(c.width, c.height, rows=(sf.row0, sf.rows))
     sf.set_initial(u, v, sm)
     stream = sf.slab.stream
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     warm = max(args.warmup, 3)
-    for _ in range(warm):
-        sf.update()
+    sf.run(warm)
     sf.sync()
     dist.barrier()
     torch.cuda.synchronize()
@@ -284,7 +323,7 @@ def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSa
             with torch.cuda.stream(stream):
                 flush.fill_(1)
             starts[k].record(stream)
-            sf.update()
+            sf.run(1)
             stops[k].record(stream)
         sf.sync()
         torch.cuda.synchronize()
@@ -323,7 +362,8 @@ def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSa
             "metric": "cell-steps/sec (n=50 SOR)", "value": value, "unit": "cell-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_block(cfg, world, {"halo_rows": halo, "exchange": "NCCL send/recv of packed edge rows",
+            "config": config_block(cfg, world, {"halo_rows": halo, "exchange": "peer-memory stores over NVLink from the library's kernels, graph-replayed step" if transport == "p2p"
+                                                else "NCCL send/recv of packed edge rows",
                                                 "halo_overflow": int(overflow[0])}),
             "roofline": {"bound": "hbm", "kernel": "whole step, all GPUs", "achieved": round(value * b_alg / 1e9, 1),
                          "peak": peak * world, "unit": "GB/s", "frac": round(value * b_alg / 1e9 / (peak * world), 4),

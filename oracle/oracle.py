@@ -44,6 +44,7 @@ def _load_oracle():
         "oracle_decay_smoke": (None, [vp, C.c_float]),
         "oracle_step": (None, [vp, srcp, C.c_float]),
         "oracle_sample_velocity": (None, [vp, C.c_int, vp, vp, vp, vp]),
+        "oracle_render_pixels": (None, [vp, vp]),
         "oracle_max_threads": (C.c_int, []),
     }
     for name, (res, args) in sig.items():
@@ -134,6 +135,12 @@ class OracleSim:
 
     def step(self, source=None, d_t=None):
         self.lib.oracle_step(self.h, self._src(source), self.cfg.d_t if d_t is None else d_t)
+
+    def render_pixels(self, prefill: int = 0) -> np.ndarray:
+        """RGBA8888 frame (H, W) uint32 of the current state (graphics_handler.cu:258-302)."""
+        out = np.full(self.shape, prefill, np.uint32)
+        self.lib.oracle_render_pixels(self.h, out.ctypes.data)
+        return out
 
     def sample_velocity(self, xs, ys):
         xs = np.ascontiguousarray(xs, np.float32)

@@ -430,6 +430,67 @@ void oracle_step(oracle_sim* s, const sayal_source* src, float d_t) {
   }
 }
 
+/* ---- frame read-back: GraphicsHandler::update_fluid_pixels (graphics_handler.cu:214-302) with
+ * hsv_to_rgb / map_rgba / clamp (helper.cu:3-51).  Pixel (x = i, y = H-1-j) sits at y*W + x, i.e. the pixel
+ * array has the same layout as the fields.  static_cast<uint8_t>(float) is what nvcc emits for it:
+ * cvt.rzi.u32.f32 (saturating, NaN -> 0) and the low 8 bits. */
+static inline uint32_t f2u8(float x) {
+  uint32_t u;
+  if (!(x > 0.0f)) u = 0; /* negative, -0, NaN */
+  else if (x >= 4294967296.0f) u = 0xffffffffu;
+  else u = (uint32_t)x;
+  return u & 255u;
+}
+
+static inline uint32_t map_rgba(uint32_t r, uint32_t g, uint32_t b, uint32_t a) { return r << 24 | g << 16 | b << 8 | a; }
+
+static inline float clampf(float x, float lo, float hi) { return (x < lo) ? lo : (x > hi) ? hi : x; }
+
+static void hsv_to_rgb(float h, float s, float v, uint32_t* r, uint32_t* g, uint32_t* b) {
+  float c = v * s;
+  float x = c * (1.0f - fabsf(fmodf(h / 60.0f, 2.0f) - 1.0f));
+  float m = v - c;
+  float r_, g_, b_;
+  if (h < 60) { r_ = c; g_ = x; b_ = 0; }
+  else if (h < 120) { r_ = x; g_ = c; b_ = 0; }
+  else if (h < 180) { r_ = 0; g_ = c; b_ = x; }
+  else if (h < 240) { r_ = 0; g_ = x; b_ = c; }
+  else if (h < 300) { r_ = x; g_ = 0; b_ = c; }
+  else { r_ = c; g_ = 0; b_ = x; }
+  *r = f2u8((r_ + m) * 255.0f);
+  *g = f2u8((g_ + m) * 255.0f);
+  *b = f2u8((b_ + m) * 255.0f);
+}
+
+void oracle_render_pixels(oracle_sim* s, uint32_t* pixels) {
+  const size_t n = (size_t)s->W * s->H;
+  const int P = s->c.enable_pressure != 0, S = s->c.enable_smoke != 0;
+  const float mn = s->min_p, mx = s->max_p;
+  for (size_t k = 0; k < n; k++) {
+    if (s->is_solid[k]) { pixels[k] = map_rgba(80, 80, 80, 255); continue; }
+    if (P) {
+      float pr = s->p[k], norm_p;
+      if (S) { /* update_smoke_and_pressure (:221-238) */
+        norm_p = 0;
+        if (pr < 0 && mn != 0) norm_p = -pr / mn;
+        else if (mx != 0) norm_p = pr / mx;
+      } else { /* update_pressure_pixel (:240-256) */
+        if (pr < 0) norm_p = -pr / mn;
+        else norm_p = pr / mx;
+      }
+      norm_p = clampf(norm_p, -1.0f, 1.0f);
+      float hue = (1.0f - norm_p) * 120.0f;
+      uint32_t r, g, b;
+      hsv_to_rgb(hue, 1.0f, S ? s->smoke[k] : 1.0f, &r, &g, &b);
+      pixels[k] = map_rgba(r, g, b, 255);
+    } else if (S) { /* update_smoke_pixels (:214-219) */
+      uint32_t color = (255u - f2u8(s->smoke[k] * 255.0f)) & 255u;
+      pixels[k] = map_rgba(255, color, color, 255);
+    }
+    /* neither: the reference leaves the pixel untouched */
+  }
+}
+
 int oracle_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

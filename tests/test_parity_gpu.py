@@ -81,7 +81,7 @@ def test_forces_bit_exact():
 
 
 @pytest.mark.parametrize("name", list(CONFIGS))
-@pytest.mark.parametrize("kernel", [0, 1, 2])
+@pytest.mark.parametrize("kernel", [0, 1])
 def test_projection_bit_exact(name, kernel):
     cfg = CONFIGS[name]()
     cfg["sim.enable_pressure"] = 0
@@ -92,7 +92,7 @@ def test_projection_bit_exact(name, kernel):
     assert_same(gpu, cpu, names=("u", "v"), what=f"projection kernel={kernel}")
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1])
 @pytest.mark.parametrize("rows", [8, 10, 12])
 @pytest.mark.parametrize("T", [1, 2, 3, 4, 5, 8, 12, 16])
 def test_tiled_projection_any_temporal_block(T, rows, kernel):
@@ -299,7 +299,7 @@ def test_large_grid_properties_3840x2160():
     cfg = baseline_config(2)
     u, v, sm = synthetic_fields(3840, 2160)
     outs = []
-    for kernel in (0, 1, 2):
+    for kernel in (0, 1):
         f = Fluid(cfg)
         f.set_field("u", u)
         f.set_field("v", v)
@@ -308,7 +308,6 @@ def test_large_grid_properties_3840x2160():
         outs.append((f.get_field("u"), f.get_field("v"), f.is_solid))
         f.close()
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
-    assert np.array_equal(outs[0][0], outs[2][0]) and np.array_equal(outs[0][1], outs[2][1])
     uu, vv, solid = outs[1]
 
     def mean_div(a, b):

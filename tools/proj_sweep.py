@@ -18,7 +18,7 @@ if (W, H) == (1920, 1080):
     cfg = baseline_config(1)
 u, v, sm = synthetic_fields(W, H)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for kernel in arg("--kernels", "1,2"):
+for kernel in arg("--kernels", "1"):
     for rows in arg("--rows", "8,10,12"):
         for T in arg("--T", "4,5,6,7,8,10,12"):
             f = Fluid(cfg)

@@ -13,7 +13,7 @@ cfg = baseline_config(1) if (W, H) == (1920, 1080) else baseline_config(1, width
 u, v, sm = synthetic_fields(W, H)
 f = Fluid(cfg)
 f.set_field("u", u); f.set_field("v", v)
-f.set_option("projection_kernel", 2); f.set_option("autotune", 0)
+f.set_option("projection_kernel", 1); f.set_option("autotune", 0)
 f.set_option("temporal_block", T); f.set_option("tile_rows_per_warp", rows)
 f.set_option("debug_timeline", 1)
 for rep in range(3):
