@@ -54,6 +54,9 @@ static void free_sim(Sim* s) {
     if (s->ipc_opened[k]) cudaIpcCloseMemHandle(s->ipc_opened[k]);
   if (s->link_block) cudaFree(s->link_block);
   if (s->link_counters) cudaFree(s->link_counters);
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+  if (s->ev_join) cudaEventDestroy(s->ev_join);
+  if (s->aux_stream) cudaStreamDestroy(s->aux_stream);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -135,6 +138,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   s->use_graph = 1;
   s->use_pdl = 1;
   s->advect_kernel = 2;
+  s->overlap_exchange = 1;
   s->autotune = 1;
   s->plan_variant = -1, s->n_plans = 0;
   s->force_variant = -1;
@@ -146,6 +150,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   if (const char* e = getenv("SAYAL_PROJECTION_KERNEL")) s->projection_kernel = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_USE_GRAPH")) s->use_graph = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_ADVECT_KERNEL")) { int k = atoi(e); if (k >= 0 && k <= 2) s->advect_kernel = k; }
+  if (const char* e = getenv("SAYAL_OVERLAP_EXCHANGE")) s->overlap_exchange = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_USE_PDL")) s->use_pdl = atoi(e) != 0;
 
   auto fail = [&](int code) {
@@ -154,6 +159,12 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   };
   cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) return fail(set_error(SAYAL_ECUDA, cudaGetErrorString(e)));
+  if (s->slab_halo > 0) {  // slabs: a second stream for exchanges that overlap interior compute
+    e = cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming);
+    if (e != cudaSuccess) return fail(set_error(SAYAL_ECUDA, cudaGetErrorString(e)));
+  }
   size_t bytes = field_elems(s) * sizeof(float);
   float** fields[] = {&s->u, &s->v, &s->p, &s->smoke, &s->u_buf, &s->v_buf, &s->smoke_buf};
   for (float** f : fields) {
@@ -188,10 +199,47 @@ static void swap_ptr(float*& a, float*& b) {
   b = t;
 }
 
-static int projection(Sim* s, int iterations, float d_t) {
+static int projection(Sim* s, int iterations, float d_t, int exchange_mask = 0) {
   if (iterations <= 0) return SAYAL_OK;
-  if (s->projection_kernel == 1) return launch_projection_tiled(s, iterations, d_t);
-  return launch_projection_plain(s, iterations, d_t);
+  if (s->projection_kernel == 1) return launch_projection_tiled(s, iterations, d_t, exchange_mask);
+  TRY(launch_projection_plain(s, iterations, d_t));
+  if (exchange_mask) TRY(launch_slab_exchange(s, exchange_mask));
+  return SAYAL_OK;
+}
+
+// Advection of a linked slab: the rows next to the slab edges first, then the exchange of the NEW arrays on the
+// aux stream while the interior rows are still being advected.
+static int advect_linked(Sim* s, float d_t, bool smoke) {
+  const Grid& g = s->g;
+  const int halo = s->slab_halo, lo = g.own_lo, hi = g.own_hi;
+  const bool overlap = s->overlap_exchange && s->aux_stream && s->advect_kernel == 2 && g.h == 1 && hi - lo >= 4 * halo;
+  const int mask = smoke ? 4 : (1 | 2);
+  if (overlap) {
+    TRY(launch_advect_geo_rows(s, d_t, smoke, lo, lo + halo));
+    TRY(launch_advect_geo_rows(s, d_t, smoke, hi - halo, hi));
+    CUDA_TRY(cudaEventRecord(s->ev_fork, s->stream));
+    CUDA_TRY(cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0));
+    TRY(launch_advect_geo_rows(s, d_t, smoke, lo + halo, hi - halo));
+  } else {
+    TRY(s->advect_kernel == 2 ? launch_advect_geo(s, d_t, !smoke, smoke)
+        : s->advect_kernel == 1 ? launch_advect_tile(s, d_t, !smoke, smoke) : launch_advect(s, d_t, !smoke, smoke));
+  }
+  if (smoke) {
+    float* t = s->smoke; s->smoke = s->smoke_buf; s->smoke_buf = t;
+    s->parity ^= 2;
+  } else {
+    float* t = s->u; s->u = s->u_buf; s->u_buf = t;
+    t = s->v; s->v = s->v_buf; s->v_buf = t;
+    s->parity ^= 1;
+  }
+  if (overlap) {
+    TRY(launch_slab_exchange_on(s, mask, s->aux_stream));
+    CUDA_TRY(cudaEventRecord(s->ev_join, s->aux_stream));
+    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+  } else {
+    TRY(launch_slab_exchange(s, mask));
+  }
+  return SAYAL_OK;
 }
 
 static int advect_velocity(Sim* s, float d_t) {
@@ -226,8 +274,7 @@ static int step_impl(Sim* s, const sayal_source* src, float d_t) {
     const int per = s->slab_halo / 2;
     for (int done = 0; done < s->cfg.proj_n;) {
       int k = s->cfg.proj_n - done < per ? s->cfg.proj_n - done : per;
-      TRY(projection(s, k, d_t));
-      TRY(launch_slab_exchange(s, 1 | 2));
+      TRY(projection(s, k, d_t, 1 | 2));
       done += k;
     }
   }
@@ -236,11 +283,12 @@ static int step_impl(Sim* s, const sayal_source* src, float d_t) {
     s->range_valid = false;
   }
   TRY(launch_extrapolation(s));
-  TRY(advect_velocity(s, d_t));
-  if (linked) TRY(launch_slab_exchange(s, 1 | 2));
-  if (s->ph.enable_smoke && s->ph.wt_smoke != 0.f) {
-    TRY(advect_smoke(s, d_t));  // decay fused (fluid.cu:792)
-    if (linked) TRY(launch_slab_exchange(s, 4));
+  if (!linked) {
+    TRY(advect_velocity(s, d_t));
+    if (s->ph.enable_smoke && s->ph.wt_smoke != 0.f) TRY(advect_smoke(s, d_t));  // decay fused (fluid.cu:792)
+  } else {
+    TRY(advect_linked(s, d_t, false));
+    if (s->ph.enable_smoke && s->ph.wt_smoke != 0.f) TRY(advect_linked(s, d_t, true));
   }
   return SAYAL_OK;
 }
@@ -528,6 +576,8 @@ int sayal_set_option(sayal_sim* sim, const char* key, int64_t value) {
   } else if (!strcmp(key, "advect_kernel")) {
     if (value < 0 || value > 2) return set_error(SAYAL_EINVAL, "advect_kernel must be 0, 1 or 2");
     s->advect_kernel = (int)value;
+  } else if (!strcmp(key, "overlap_exchange")) {
+    s->overlap_exchange = value != 0;
   } else if (!strcmp(key, "use_pdl")) {
     s->use_pdl = value != 0;
   } else if (!strcmp(key, "debug_timeline")) {  // profiling only: per-CTA phase timestamps (sayal_debug_timeline)

@@ -108,6 +108,9 @@ struct Sim {
   unsigned* link_counters;  // private
   SlabLinkDev link;
   void* ipc_opened[2];      // peer blocks opened with cudaIpcOpenMemHandle (closed on destroy)
+  cudaStream_t aux_stream;  // exchange kernels run here, concurrently with interior compute
+  cudaEvent_t ev_fork, ev_join;
+  int overlap_exchange;     // option: overlap exchanges with interior compute (default 1)
 };
 
 // ---- kernels_basic.cu ---------------------------------------------------------------------------
@@ -126,15 +129,17 @@ int launch_pack_rows(Sim* s, int local_row0, int nrows, int field_mask, float* d
 int launch_build_geo(Sim* s);
 int launch_advect_tile(Sim* s, float d_t, bool velocity, bool smoke);
 int launch_advect_geo(Sim* s, float d_t, bool velocity, bool smoke);
+int launch_advect_geo_rows(Sim* s, float d_t, bool smoke, int row_lo, int row_hi);  // local rows [row_lo, row_hi)
 
 // ---- slab_exchange.cu -----------------------------------------------------------------------------
 int slab_link_alloc(Sim* s);
 int slab_link_connect(Sim* s, int side, void* peer_block, size_t peer_stage_elems);
 size_t slab_link_stage_elems(const Sim* s);
 int launch_slab_exchange(Sim* s, int field_mask);
+int launch_slab_exchange_on(Sim* s, int field_mask, cudaStream_t stream);
 
 // ---- projection_pack.cu --------------------------------------------------------------------------
-int launch_projection_tiled(Sim* s, int iterations, float d_t);
+int launch_projection_tiled(Sim* s, int iterations, float d_t, int exchange_mask = 0);
 int tiled_max_temporal_block();
 int tiled_prepare(Sim* s, int iterations);  // choose the tile plan (may time candidates; not capturable)
 

@@ -4,14 +4,14 @@
 // One process per GPU.  Each sim owns ONE device block that neighbours may write: a flag word and a
 // double-buffered receive area per side.  The block's CUDA IPC handle is handed to the two neighbour processes
 // once (sayal_slab_ipc_export / sayal_slab_ipc_connect; slabs of one process link with sayal_slab_connect_local).
-// After that an exchange is two kernels on the sim's own stream and nothing else — no host synchronisation, no
+// After that an exchange is ONE kernel on the sim's own stream and nothing else — no host synchronisation, no
 // collective library, capturable in the step's CUDA graph:
 //
-//   push         reads this slab's `halo` edge rows of the selected fields and stores them straight into the
-//                neighbour's receive area (posted NVLink writes), fences, and the last CTA to finish publishes
-//                the exchange's sequence number in the neighbour's flag word (st.release.sys).
-//   wait_unpack  spins (ld.acquire.sys on a LOCAL word) until the neighbour's push with the expected sequence
-//                number has landed, then copies the receive area into the ghost rows.
+//   push   reads this slab's `halo` edge rows of the selected fields and stores them straight into the
+//          neighbour's receive area (posted NVLink writes), fences, and the last CTA to finish publishes the
+//          exchange's sequence number in the neighbour's flag word (st.release.sys);
+//   wait   spins (ld.acquire.sys on a LOCAL word) until the neighbour's push with the same sequence number has
+//          landed, then copies the receive area into the ghost rows.
 //
 // Sequence numbers live in device memory and are advanced by the kernels themselves, so a captured graph can be
 // replayed.  The receive area is double-buffered by sequence parity; a buffer is reused two exchanges later,
@@ -26,7 +26,7 @@ namespace sayal {
 
 namespace {
 
-constexpr int XTHREADS = 256;
+constexpr int XTHREADS = 1024;
 constexpr long long kSpinLimitNs = 2000000000ll;
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
@@ -77,35 +77,29 @@ __device__ __forceinline__ void copy_rows(const Grid& g, const Fields3& fs, int 
   }
 }
 
-// grid (blocks, 2): blockIdx.y = side (0 = low memory rows, 1 = high memory rows)
-__global__ void __launch_bounds__(XTHREADS) slab_push_kernel(Grid g, int halo, Fields3 fs, SlabLinkDev d) {
+// One exchange, one kernel.  grid (blocks, 2): blockIdx.y = side (0 = low memory rows, 1 = high memory rows).
+//   push: every CTA stores its share of this slab's edge rows into the neighbour's receive area; one thread per
+//         CTA then fences at system scope (the CTA barrier orders the other threads' stores before it) and takes a
+//         ticket; the last CTA publishes the sequence number in the neighbour's flag word.
+//   wait: one thread per CTA spins on the LOCAL flag word until the neighbour's push of the same exchange has
+//         landed, then the CTA copies its share of the receive area into the ghost rows.
+__global__ void __launch_bounds__(XTHREADS) slab_exchange_kernel(Grid g, int halo, Fields3 fs, SlabLinkDev d) {
   const int side = blockIdx.y;
   if (!d.peer_recv[side]) return;
-  const unsigned seq = d.send_seq[side];  // advanced below by the last CTA, after every CTA has read it
+  const unsigned seq = d.send_seq[side];  // == recv_seq: advanced below by the last CTA, after every CTA has read it
   float* dst = d.peer_recv[side] + (size_t)(seq & 1u) * d.stage_elems;
-  const int row0 = side == 0 ? g.own_lo : g.own_hi - halo;
-  copy_rows<false>(g, fs, row0, halo, dst, blockIdx.x, gridDim.x);
-  __threadfence_system();
+  copy_rows<false>(g, fs, side == 0 ? g.own_lo : g.own_hi - halo, halo, dst, blockIdx.x, gridDim.x);
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     unsigned t = atomicAdd(&d.ticket[side], 1u);
     if (t == gridDim.x - 1) {
       d.ticket[side] = 0;
-      d.send_seq[side] = seq + 1;
       __threadfence_system();
       st_release_sys(d.peer_flag[side], seq + 1);
     }
-  }
-}
-
-__global__ void __launch_bounds__(XTHREADS) slab_wait_unpack_kernel(Grid g, int halo, Fields3 fs, SlabLinkDev d) {
-  const int side = blockIdx.y;
-  if (!d.peer_recv[side]) return;
-  const unsigned seq = d.recv_seq[side];
-  if (threadIdx.x == 0) {
     const long long t0 = now_ns();
     while ((int)(ld_acquire_sys(d.my_flag + side) - (seq + 1)) < 0) {
-      __nanosleep(64);
       if (now_ns() - t0 > kSpinLimitNs) {  // neighbour gone: do not hang the GPU
         atomicExch(d.link_error, 1);
         break;
@@ -114,14 +108,13 @@ __global__ void __launch_bounds__(XTHREADS) slab_wait_unpack_kernel(Grid g, int 
   }
   __syncthreads();
   const float* src = d.my_recv[side] + (size_t)(seq & 1u) * d.stage_elems;
-  const int row0 = side == 0 ? g.own_lo - halo : g.own_hi;
-  copy_rows<true>(g, fs, row0, halo, const_cast<float*>(src), blockIdx.x, gridDim.x);
+  copy_rows<true>(g, fs, side == 0 ? g.own_lo - halo : g.own_hi, halo, const_cast<float*>(src), blockIdx.x, gridDim.x);
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned t = atomicAdd(&d.ticket[2 + side], 1u);
     if (t == gridDim.x - 1) {
       d.ticket[2 + side] = 0;
-      d.recv_seq[side] = seq + 1;
+      d.send_seq[side] = seq + 1;
     }
   }
 }
@@ -174,7 +167,9 @@ int slab_link_connect(Sim* s, int side, void* peer_block, size_t peer_stage_elem
 
 size_t slab_link_stage_elems(const Sim* s) { return stage_elems(s); }
 
-int launch_slab_exchange(Sim* s, int field_mask) {
+int launch_slab_exchange(Sim* s, int field_mask) { return launch_slab_exchange_on(s, field_mask, s->stream); }
+
+int launch_slab_exchange_on(Sim* s, int field_mask, cudaStream_t stream) {
   SlabLinkDev& d = s->link;
   if (!s->link_block || (!d.peer_recv[0] && !d.peer_recv[1])) return SAYAL_OK;  // no neighbours: nothing to do
   Fields3 fs;
@@ -187,15 +182,12 @@ int launch_slab_exchange(Sim* s, int field_mask) {
   size_t items = (size_t)s->slab_halo * s->g.W * fs.n / 4;
   int blocks = (int)((items + XTHREADS - 1) / XTHREADS);
   if (blocks < 1) blocks = 1;
-  // at most 32 CTAs per side: the waiting CTAs of one slab must never fill the GPU, or a second slab sharing the
-  // device (tests; several slabs per GPU) could not run the kernels the wait is waiting for
-  if (blocks > 32) blocks = 32;
-  slab_push_kernel<<<dim3(blocks, 2), XTHREADS, 0, s->stream>>>(s->g, s->slab_halo, fs, d);
+  // at most 8 fat CTAs per side: the exchange shares the GPU with the interior tiles it overlaps with, and the
+  // waiting CTAs of one slab must never fill the device, or a second slab on the same device (tests) could not
+  // run the kernels the wait is waiting for
+  if (blocks > 8) blocks = 8;
+  slab_exchange_kernel<<<dim3(blocks, 2), XTHREADS, 0, stream>>>(s->g, s->slab_halo, fs, d);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_error(SAYAL_ECUDA, cudaGetErrorString(e));
-  s->launches++;
-  slab_wait_unpack_kernel<<<dim3(blocks, 2), XTHREADS, 0, s->stream>>>(s->g, s->slab_halo, fs, d);
-  e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(SAYAL_ECUDA, cudaGetErrorString(e));
   s->launches++;
   return SAYAL_OK;

@@ -148,6 +148,21 @@ def test_native_linked_slabs_bit_identical_to_single_gpu(world, halo, graph):
         assert np.array_equal(got[n], want[n]), n
 
 
+@pytest.mark.parametrize("overlap", [0, 1])
+def test_native_slabs_tall_domain_split_last_pass(overlap, monkeypatch):
+    """Tall slabs (several tile rows each): with overlap on, the last projection pass of a chunk runs as edge tile
+    rows + interior tile rows with the exchange in between on the aux stream; advection likewise.  Same bits."""
+    monkeypatch.setenv("SAYAL_OVERLAP_EXCHANGE", str(overlap))
+    cfg = baseline_config(1, width=256, height=1400)
+    cfg["sim.projection.n"] = 21
+    cfg["sim.wind_tunnel.speed"] = 60.0
+    want, _ = run_single(cfg, 2)
+    got, overflow, errors = run_slabs_native(cfg, 2, 20, 2, graph=1)
+    assert errors == 0 and overflow == 0
+    for n in ("u", "v", "smoke"):
+        assert np.array_equal(got[n], want[n]), n
+
+
 def test_unlinked_slab_refuses_to_step():
     from opensayal_b200 import SayalError
     cfg = baseline_config(1, width=256, height=256)
