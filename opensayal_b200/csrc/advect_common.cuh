@@ -39,13 +39,13 @@ __device__ __forceinline__ float pos_half(int k, int h) {
 __device__ __forceinline__ bool base_fluid(const Grid& g, const View& w, int i, int j, long* k) {
   if (i < 0 || j < 0 || i >= g.W || j >= g.H) return false;
   int lr = (g.H - 1 - j) - g.row_base;
-  if (lr < 0 || lr >= g.local_rows) {  // a slab's back-trace left its ghost rows: report, do not guess
+  if (lr < g.valid_lo || lr >= g.valid_hi) {  // a slab's back-trace left its ghost rows: report, do not guess
     atomicAdd(w.overflow, 1);
     return false;
   }
   long kk = (long)lr * g.pitch + i;
   if (w.flags[kk] & FL_SOLID) return false;
-  if (lr < 1 || lr > g.local_rows - 2) {  // fluid cell on the first/last local row: only possible in a slab
+  if (lr < g.valid_lo + 1 || lr > g.valid_hi - 2) {  // fluid cell on the first/last local row: only possible in a slab
     atomicAdd(w.overflow, 1);
     return false;
   }
@@ -127,7 +127,7 @@ __device__ SAYAL_SAMPLER_ATTR float general_velocity_x(const Grid& g, const View
 __device__ __forceinline__ bool fluid_at(const Grid& g, const View& w, int i, int j, long* k) {
   if (i < 0 || j < 0 || i >= g.W || j >= g.H) return false;
   int lr = (g.H - 1 - j) - g.row_base;
-  if (lr < 0 || lr >= g.local_rows) {
+  if (lr < g.valid_lo || lr >= g.valid_hi) {
     atomicAdd(w.overflow, 1);
     return false;
   }
@@ -160,7 +160,7 @@ __device__ SAYAL_SAMPLER_ATTR float interpolate_smoke(const Grid& g, const View&
   // the common case: base cell is an interior cell => no bounds tests
   bool interior = i >= 1 && j >= 1 && i <= g.W - 2 && j <= g.H - 2;
   int lr = (g.H - 1 - j) - g.row_base;
-  if (interior && lr >= 1 && lr <= g.local_rows - 2) {
+  if (interior && lr >= g.valid_lo + 1 && lr <= g.valid_hi - 2) {
     long k = (long)lr * g.pitch + i;
     long kj = -(long)dj * g.pitch;  // (i, j+dj)
 #pragma unroll

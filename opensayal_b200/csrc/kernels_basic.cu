@@ -331,8 +331,8 @@ advect_velocity_kernel(Grid g, View w, float d_t, float* __restrict__ u_out, flo
   const long up = -(long)g.pitch, down = (long)g.pitch;
   // which neighbours exist at all (index_is_valid, fluid.cu:356-358); rows must also be held locally
   const bool has_l = i > 0, has_r = i < g.W - 1;
-  const bool has_up = j < g.H - 1 && lr > 0, has_dn = j > 0 && lr < g.local_rows - 1;
-  if ((j < g.H - 1 && lr == 0) || (j > 0 && lr == g.local_rows - 1)) atomicAdd(w.overflow, 1);
+  const bool has_up = j < g.H - 1 && lr > g.valid_lo, has_dn = j > 0 && lr < g.valid_hi - 1;
+  if ((j < g.H - 1 && lr == g.valid_lo) || (j > 0 && lr == g.valid_hi - 1)) atomicAdd(w.overflow, 1);
   float uk = w.u[k], vk = w.v[k];
   // get_vertical_edge_velocity (fluid.cu:364-389)
   float avg_v = vk;

@@ -143,8 +143,6 @@ struct PackArgs {
   int stride_x;  // TW - 2*halo_x
   int stride_y;  // TH - 2*halo_y
   long long* timeline;  // profiling only (option "debug_timeline"): 5 x int64 per CTA, or null
-  int ty_mode;    // which tile rows this launch covers: 0 all, 1 the first and the last, 2 all but those
-  int tiles_y;    // tile rows of the whole pass
 };
 
 __device__ __forceinline__ long long globaltimer() {
@@ -235,11 +233,10 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
 
   const Grid& g = a.g;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int tile_y = a.ty_mode == 0 ? blockIdx.y : (a.ty_mode == 1 ? (blockIdx.y ? a.tiles_y - 1 : 0) : blockIdx.y + 1);
-  const int X0 = blockIdx.x * a.stride_x, Y0 = tile_y * a.stride_y;
+  const int X0 = blockIdx.x * a.stride_x, Y0 = blockIdx.y * a.stride_y;
   const int x = X0 + 4 * lane;
   const int lr0 = Y0 + w * RY;
-  long long* tl = a.timeline ? a.timeline + 5 * (size_t)(tile_y * gridDim.x + blockIdx.x) : nullptr;
+  long long* tl = a.timeline ? a.timeline + 5 * (size_t)(blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
   if (tl && threadIdx.x == 0) {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -464,13 +461,8 @@ int launch_pass(Sim* s, const Variant& v, const PackArgs& a, dim3 grid, cudaStre
   return SAYAL_OK;
 }
 
-// `exchange_mask` != 0 (linked slabs): the ghost-row exchange that follows the projection is issued from here.
-// When the geometry allows, the LAST pass runs as two launches — the first and last tile rows, which produce
-// every row a neighbour needs, then the interior tile rows — and the exchange kernel runs on the aux stream
-// concurrently with the interior launch, so its NVLink latency hides behind compute.
-int run_passes(Sim* s, int variant, int T, int iterations, int exchange_mask) {
+int run_passes(Sim* s, int variant, int T, int iterations) {
   const Variant& v = kVariants[variant];
-  const int th = v.ry * v.nw;
   int done = 0;
   while (done < iterations) {
     int it = iterations - done < T ? iterations - done : T;
@@ -492,42 +484,12 @@ int run_passes(Sim* s, int variant, int T, int iterations, int exchange_mask) {
     a.timeline = s->d_timeline;  // the last pass wins: profile single passes
     if (s->d_timeline && (size_t)q.tiles_x * q.tiles_y * 5 > s->timeline_cap) a.timeline = nullptr;
     s->timeline_tiles = a.timeline ? q.tiles_x * q.tiles_y : 0;
-    a.ty_mode = 0;
-    a.tiles_y = q.tiles_y;
-    const bool last = done + it >= iterations;
-    // rows the neighbours need: [own_lo, own_lo + halo) and [own_hi - halo, own_hi).  The first tile row writes
-    // local rows [0, th - halo_y), the last one [(tiles_y-1)*stride_y + halo_y, local_rows).
-    bool split = last && exchange_mask && s->overlap_exchange && s->aux_stream && q.tiles_y >= 3 &&
-                 s->g.own_lo + s->slab_halo <= th - q.halo_y &&
-                 s->g.own_hi - s->slab_halo >= (q.tiles_y - 1) * q.stride_y + q.halo_y;
-    if (!split) {
-      int r = launch_pass(s, v, a, dim3(q.tiles_x, q.tiles_y), s->stream);
-      if (r != SAYAL_OK) return r;
-    } else {
-      a.ty_mode = 1;
-      int r = launch_pass(s, v, a, dim3(q.tiles_x, 2), s->stream);
-      if (r != SAYAL_OK) return r;
-      if (cudaEventRecord(s->ev_fork, s->stream) != cudaSuccess || cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0) != cudaSuccess)
-        return set_error(SAYAL_ECUDA, "projection: fork to the exchange stream failed");
-      a.ty_mode = 2;
-      r = launch_pass(s, v, a, dim3(q.tiles_x, q.tiles_y - 2), s->stream);
-      if (r != SAYAL_OK) return r;
-    }
+    int r = launch_pass(s, v, a, dim3(q.tiles_x, q.tiles_y), s->stream);
+    if (r != SAYAL_OK) return r;
     float* t = s->u; s->u = s->u_buf; s->u_buf = t;  // ping-pong: neighbouring tiles still read the old halo
     t = s->v; s->v = s->v_buf; s->v_buf = t;
     s->parity ^= 1;
     done += it;
-    if (last && exchange_mask) {
-      if (split) {
-        int r = launch_slab_exchange_on(s, exchange_mask, s->aux_stream);
-        if (r != SAYAL_OK) return r;
-        if (cudaEventRecord(s->ev_join, s->aux_stream) != cudaSuccess || cudaStreamWaitEvent(s->stream, s->ev_join, 0) != cudaSuccess)
-          return set_error(SAYAL_ECUDA, "projection: join from the exchange stream failed");
-      } else {
-        int r = launch_slab_exchange(s, exchange_mask);
-        if (r != SAYAL_OK) return r;
-      }
-    }
   }
   return SAYAL_OK;
 }
@@ -584,7 +546,7 @@ int tiled_prepare(Sim* s, int iterations) {
         float ms_min = 1e30f;
         for (int rep = 0; rep < 3; rep++) {  // first repetition warms the instruction cache
           cudaEventRecord(e0, s->stream);
-          int r = run_passes(s, cands[c].variant, cands[c].T, iterations, 0);
+          int r = run_passes(s, cands[c].variant, cands[c].T, iterations);
           cudaEventRecord(e1, s->stream);
           if (r != SAYAL_OK || cudaEventSynchronize(e1) != cudaSuccess) { ms_min = 1e30f; break; }
           float ms = 0.f;
@@ -615,15 +577,11 @@ int tiled_prepare(Sim* s, int iterations) {
   return SAYAL_OK;
 }
 
-int launch_projection_tiled(Sim* s, int iterations, float d_t, int exchange_mask) {
-  if (s->ph.enable_pressure) {  // pressure accumulates per cell: plain path
-    int r = launch_projection_plain(s, iterations, d_t);
-    if (r == SAYAL_OK && exchange_mask) r = launch_slab_exchange(s, exchange_mask);
-    return r;
-  }
+int launch_projection_tiled(Sim* s, int iterations, float d_t) {
+  if (s->ph.enable_pressure) return launch_projection_plain(s, iterations, d_t);  // pressure accumulates per cell: plain path
   int r = tiled_prepare(s, iterations);
   if (r != SAYAL_OK) return r;
-  return run_passes(s, s->plan_variant, s->plan_T, iterations, exchange_mask);
+  return run_passes(s, s->plan_variant, s->plan_T, iterations);
 }
 
 }  // namespace sayal

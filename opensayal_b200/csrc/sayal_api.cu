@@ -110,6 +110,8 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
     g.own_lo = 0;
     g.own_hi = c->height;
   }
+  g.valid_lo = 0;
+  g.valid_hi = g.local_rows;
   Phys& p = s->ph;
   p.o = c->proj_o;
   p.density = c->density;
@@ -139,6 +141,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   s->use_pdl = 1;
   s->advect_kernel = 2;
   s->overlap_exchange = 1;
+  s->advect_margin = 16;
   s->autotune = 1;
   s->plan_variant = -1, s->n_plans = 0;
   s->force_variant = -1;
@@ -150,6 +153,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   if (const char* e = getenv("SAYAL_PROJECTION_KERNEL")) s->projection_kernel = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_USE_GRAPH")) s->use_graph = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_ADVECT_KERNEL")) { int k = atoi(e); if (k >= 0 && k <= 2) s->advect_kernel = k; }
+  if (const char* e = getenv("SAYAL_ADVECT_MARGIN")) { int m = atoi(e); if (m >= 2) s->advect_margin = m; }
   if (const char* e = getenv("SAYAL_OVERLAP_EXCHANGE")) s->overlap_exchange = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_USE_PDL")) s->use_pdl = atoi(e) != 0;
 
@@ -199,47 +203,10 @@ static void swap_ptr(float*& a, float*& b) {
   b = t;
 }
 
-static int projection(Sim* s, int iterations, float d_t, int exchange_mask = 0) {
+static int projection(Sim* s, int iterations, float d_t) {
   if (iterations <= 0) return SAYAL_OK;
-  if (s->projection_kernel == 1) return launch_projection_tiled(s, iterations, d_t, exchange_mask);
-  TRY(launch_projection_plain(s, iterations, d_t));
-  if (exchange_mask) TRY(launch_slab_exchange(s, exchange_mask));
-  return SAYAL_OK;
-}
-
-// Advection of a linked slab: the rows next to the slab edges first, then the exchange of the NEW arrays on the
-// aux stream while the interior rows are still being advected.
-static int advect_linked(Sim* s, float d_t, bool smoke) {
-  const Grid& g = s->g;
-  const int halo = s->slab_halo, lo = g.own_lo, hi = g.own_hi;
-  const bool overlap = s->overlap_exchange && s->aux_stream && s->advect_kernel == 2 && g.h == 1 && hi - lo >= 4 * halo;
-  const int mask = smoke ? 4 : (1 | 2);
-  if (overlap) {
-    TRY(launch_advect_geo_rows(s, d_t, smoke, lo, lo + halo));
-    TRY(launch_advect_geo_rows(s, d_t, smoke, hi - halo, hi));
-    CUDA_TRY(cudaEventRecord(s->ev_fork, s->stream));
-    CUDA_TRY(cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0));
-    TRY(launch_advect_geo_rows(s, d_t, smoke, lo + halo, hi - halo));
-  } else {
-    TRY(s->advect_kernel == 2 ? launch_advect_geo(s, d_t, !smoke, smoke)
-        : s->advect_kernel == 1 ? launch_advect_tile(s, d_t, !smoke, smoke) : launch_advect(s, d_t, !smoke, smoke));
-  }
-  if (smoke) {
-    float* t = s->smoke; s->smoke = s->smoke_buf; s->smoke_buf = t;
-    s->parity ^= 2;
-  } else {
-    float* t = s->u; s->u = s->u_buf; s->u_buf = t;
-    t = s->v; s->v = s->v_buf; s->v_buf = t;
-    s->parity ^= 1;
-  }
-  if (overlap) {
-    TRY(launch_slab_exchange_on(s, mask, s->aux_stream));
-    CUDA_TRY(cudaEventRecord(s->ev_join, s->aux_stream));
-    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
-  } else {
-    TRY(launch_slab_exchange(s, mask));
-  }
-  return SAYAL_OK;
+  if (s->projection_kernel == 1) return launch_projection_tiled(s, iterations, d_t);
+  return launch_projection_plain(s, iterations, d_t);
 }
 
 static int advect_velocity(Sim* s, float d_t) {
@@ -259,7 +226,62 @@ static int advect_smoke(Sim* s, float d_t) {
   return SAYAL_OK;
 }
 
-// Fluid::update (fluid.cu:770-795)
+// Local rows that are exact when the ghost rows are valid to depth `depth` beyond the owned rows.
+static void set_valid_depth(Sim* s, int depth) {
+  Grid& g = s->g;
+  g.valid_lo = g.own_lo - depth < 0 ? 0 : g.own_lo - depth;
+  g.valid_hi = g.own_hi + depth > g.local_rows ? g.local_rows : g.own_hi + depth;
+}
+
+static int advect_rows(Sim* s, float d_t, bool smoke, int lo, int hi) {
+  if (s->advect_kernel == 2 && s->g.h == 1) return launch_advect_geo_rows(s, d_t, smoke, lo, hi);
+  // the other kernels advect [own_lo, own_hi): narrow / widen that window for the call
+  Grid saved = s->g;
+  s->g.own_lo = lo;
+  s->g.own_hi = hi;
+  int r = s->advect_kernel == 1 ? launch_advect_tile(s, d_t, !smoke, smoke) : launch_advect(s, d_t, !smoke, smoke);
+  s->g.own_lo = saved.own_lo;
+  s->g.own_hi = saved.own_hi;
+  return r;
+}
+
+// Advection of a linked slab.  `ghost` extra rows beyond the owned ones are advected too (the smoke sampler
+// reads the NEW velocity one row above the cell).  With `exchange_mask` the stage ends the step: the rows next
+// to the slab edges are advected first and the exchange of the new arrays runs on the aux stream while the
+// interior rows are still being advected.
+static int advect_linked(Sim* s, float d_t, bool smoke, int ghost, int exchange_mask) {
+  const Grid& g = s->g;
+  const int halo = s->slab_halo;
+  const int lo = g.own_lo - ghost < 0 ? 0 : g.own_lo - ghost;
+  const int hi = g.own_hi + ghost > g.local_rows ? g.local_rows : g.own_hi + ghost;
+  const bool overlap = exchange_mask && s->overlap_exchange && s->aux_stream && g.own_hi - g.own_lo >= 4 * halo;
+  if (overlap) {
+    TRY(advect_rows(s, d_t, smoke, lo, g.own_lo + halo));
+    TRY(advect_rows(s, d_t, smoke, g.own_hi - halo, hi));
+    CUDA_TRY(cudaEventRecord(s->ev_fork, s->stream));
+    CUDA_TRY(cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0));
+    TRY(advect_rows(s, d_t, smoke, g.own_lo + halo, g.own_hi - halo));
+  } else {
+    TRY(advect_rows(s, d_t, smoke, lo, hi));
+  }
+  if (smoke) {
+    swap_ptr(s->smoke, s->smoke_buf);
+    s->parity ^= 2;
+  } else {
+    swap_ptr(s->u, s->u_buf);
+    swap_ptr(s->v, s->v_buf);
+    s->parity ^= 1;
+  }
+  if (overlap) {
+    TRY(launch_slab_exchange_on(s, exchange_mask, s->aux_stream));
+    CUDA_TRY(cudaEventRecord(s->ev_join, s->aux_stream));
+    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+  } else if (exchange_mask) {
+    TRY(launch_slab_exchange(s, exchange_mask));
+  }
+  return SAYAL_OK;
+}
+
 bool is_linked(const Sim* s);
 
 static int step_impl(Sim* s, const sayal_source* src, float d_t) {
@@ -267,14 +289,21 @@ static int step_impl(Sim* s, const sayal_source* src, float d_t) {
   TRY(launch_forces(s, src, d_t));
   if (s->ph.enable_pressure) TRY(launch_zero_pressure(s));
   // viscosity: the reference's racy diffusion loop (fluid.cu:185-190, H1) is out of scope; see DESIGN.md
+  // y-slab (linked): ghost rows are exact to depth D beyond the owned rows; every SOR iteration costs two rows
+  // of depth, an exchange restores D = halo.  Exchanges happen only when the next operation needs more depth
+  // than is left, and once at the end of the step (u, v and smoke together).
+  int D = s->slab_halo;
   if (!linked) {
     TRY(projection(s, s->cfg.proj_n, d_t));
   } else {
-    // y-slab: `halo` ghost rows keep the owned rows exact for halo/2 iterations, then neighbours swap edge rows
-    const int per = s->slab_halo / 2;
     for (int done = 0; done < s->cfg.proj_n;) {
-      int k = s->cfg.proj_n - done < per ? s->cfg.proj_n - done : per;
-      TRY(projection(s, k, d_t, 1 | 2));
+      if (D < 2) {
+        TRY(launch_slab_exchange(s, 1 | 2));
+        D = s->slab_halo;
+      }
+      int k = s->cfg.proj_n - done < D / 2 ? s->cfg.proj_n - done : D / 2;
+      TRY(projection(s, k, d_t));
+      D -= 2 * k;
       done += k;
     }
   }
@@ -287,8 +316,21 @@ static int step_impl(Sim* s, const sayal_source* src, float d_t) {
     TRY(advect_velocity(s, d_t));
     if (s->ph.enable_smoke && s->ph.wt_smoke != 0.f) TRY(advect_smoke(s, d_t));  // decay fused (fluid.cu:792)
   } else {
-    TRY(advect_linked(s, d_t, false));
-    if (s->ph.enable_smoke && s->ph.wt_smoke != 0.f) TRY(advect_linked(s, d_t, true));
+    const bool smoke = s->ph.enable_smoke && s->ph.wt_smoke != 0.f;
+    // velocity is advected on the owned rows and one ghost row each side; its gathers reach advect_margin rows
+    if (D < s->advect_margin + 1) {
+      TRY(launch_slab_exchange(s, 1 | 2));
+      D = s->slab_halo;
+    }
+    set_valid_depth(s, D);
+    int r = advect_linked(s, d_t, false, 1, smoke ? 0 : (1 | 2));
+    if (r == SAYAL_OK && smoke) {
+      // new velocity: exact on the owned rows +- 1; smoke ghosts: exact to the full halo since the last exchange
+      r = advect_linked(s, d_t, true, 0, 1 | 2 | 4);
+    }
+    s->g.valid_lo = 0;
+    s->g.valid_hi = s->g.local_rows;
+    if (r != SAYAL_OK) return r;
   }
   return SAYAL_OK;
 }
@@ -330,7 +372,7 @@ int sayal_step(sayal_sim* sim, const sayal_source* src, float d_t) {
   if (!sim) return set_error(SAYAL_EINVAL, "sayal_step: null sim");
   Sim* s = S(sim);
   if (is_slab(s) && !is_linked(s)) return set_error(SAYAL_EINVAL, "sayal_step: a slab sim must be linked to its neighbours first (sayal_slab_ipc_connect / sayal_slab_connect_local), or stepped stage by stage");
-  if (is_linked(s) && s->slab_halo < 2) return set_error(SAYAL_EINVAL, "sayal_step: linked slabs need halo >= 2");
+  if (is_linked(s) && s->slab_halo < s->advect_margin + 1) return set_error(SAYAL_EINVAL, "sayal_step: linked slabs need halo >= advect_margin + 1 (default 17)");
   CUDA_TRY(cudaSetDevice(s->device));
   return step_impl(s, src, d_t);
 }
@@ -339,7 +381,7 @@ int sayal_run(sayal_sim* sim, int32_t steps, float d_t) {
   if (!sim) return set_error(SAYAL_EINVAL, "sayal_run: null sim");
   Sim* s = S(sim);
   if (is_slab(s) && !is_linked(s)) return set_error(SAYAL_EINVAL, "sayal_run: a slab sim must be linked to its neighbours first");
-  if (is_linked(s) && s->slab_halo < 2) return set_error(SAYAL_EINVAL, "sayal_run: linked slabs need halo >= 2");
+  if (is_linked(s) && s->slab_halo < s->advect_margin + 1) return set_error(SAYAL_EINVAL, "sayal_run: linked slabs need halo >= advect_margin + 1 (default 17)");
   if (steps < 0) return set_error(SAYAL_EINVAL, "sayal_run: steps < 0");
   CUDA_TRY(cudaSetDevice(s->device));
   if (s->graph_dt != d_t) {
@@ -350,9 +392,14 @@ int sayal_run(sayal_sim* sim, int32_t steps, float d_t) {
     if (!is_linked(s)) {
       TRY(tiled_prepare(s, s->cfg.proj_n));
     } else {
-      const int per = s->slab_halo / 2;
-      if (s->cfg.proj_n >= per) TRY(tiled_prepare(s, per));
-      if (s->cfg.proj_n % per) TRY(tiled_prepare(s, s->cfg.proj_n % per));
+      int D = s->slab_halo;
+      for (int done = 0; done < s->cfg.proj_n;) {  // the chunk sizes step_impl will use
+        if (D < 2) D = s->slab_halo;
+        int k = s->cfg.proj_n - done < D / 2 ? s->cfg.proj_n - done : D / 2;
+        TRY(tiled_prepare(s, k));
+        D -= 2 * k;
+        done += k;
+      }
     }
   }
   int remaining = steps;
@@ -576,6 +623,9 @@ int sayal_set_option(sayal_sim* sim, const char* key, int64_t value) {
   } else if (!strcmp(key, "advect_kernel")) {
     if (value < 0 || value > 2) return set_error(SAYAL_EINVAL, "advect_kernel must be 0, 1 or 2");
     s->advect_kernel = (int)value;
+  } else if (!strcmp(key, "advect_margin")) {
+    if (value < 2) return set_error(SAYAL_EINVAL, "advect_margin must be >= 2");
+    s->advect_margin = (int)value;
   } else if (!strcmp(key, "overlap_exchange")) {
     s->overlap_exchange = value != 0;
   } else if (!strcmp(key, "use_pdl")) {

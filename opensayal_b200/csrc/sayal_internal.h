@@ -36,6 +36,8 @@ struct Grid {
   int row_base;    // global memory row of local row 0
   int local_rows;  // rows held (owned + ghost)
   int own_lo, own_hi;
+  int valid_lo, valid_hi;  // local rows whose data is exact right now (slabs: ghost rows go stale between exchanges);
+                           // the advection samplers count a gather that leaves this range as halo overflow
   int h;           // Fluid::cell_size, an int (fluid.cuh:46)
 };
 
@@ -111,6 +113,7 @@ struct Sim {
   cudaStream_t aux_stream;  // exchange kernels run here, concurrently with interior compute
   cudaEvent_t ev_fork, ev_join;
   int overlap_exchange;     // option: overlap exchanges with interior compute (default 1)
+  int advect_margin;        // ghost depth the advection may gather from: ceil(max|velocity| d_t) + 2 (default 16)
 };
 
 // ---- kernels_basic.cu ---------------------------------------------------------------------------
@@ -139,7 +142,7 @@ int launch_slab_exchange(Sim* s, int field_mask);
 int launch_slab_exchange_on(Sim* s, int field_mask, cudaStream_t stream);
 
 // ---- projection_pack.cu --------------------------------------------------------------------------
-int launch_projection_tiled(Sim* s, int iterations, float d_t, int exchange_mask = 0);
+int launch_projection_tiled(Sim* s, int iterations, float d_t);
 int tiled_max_temporal_block();
 int tiled_prepare(Sim* s, int iterations);  // choose the tile plan (may time candidates; not capturable)
 

@@ -12,9 +12,14 @@ Why ghost rows are enough (and keep the result bit-identical to one GPU):
     kernels count every sample that would leave them (`halo_overflow`); a non-zero count is an error.
   * forces / extrapolation are functions of position and of the local neighbour row: applied to every held row.
 
-Per step: forces, [projection chunk, exchange(u,v)] x ceil(n / iters_per_exchange), extrapolation, velocity
-advection, exchange(u,v), smoke advection, exchange(smoke).  The exchange itself is a neighbour send/recv of
-`halo` packed rows (NCCL over NVLink between processes, a device copy between slabs of one process).
+Two schedules, both bit-identical to one GPU:
+  * `step_schedule` (driven from Python, NCCL / gloo / device-copy exchanges): forces, [projection chunk,
+    exchange(u,v)] x ceil(n / (halo/2)), extrapolation, velocity advection, exchange(u,v), smoke advection,
+    exchange(smoke).
+  * `lazy_schedule` (what the library runs natively for linked slabs, csrc/sayal_api.cu + csrc/slab_exchange.cu:
+    peer-memory stores over NVLink from its own kernels, the whole step one CUDA-graph replay): exchanges only when
+    the remaining ghost depth is too small for the next operation, plus one exchange of u, v, smoke at the end of
+    the step — ONE exchange per step when halo >= 2 n + margin + 1, hidden behind the interior smoke advection.
 
 The schedule is data (a list of ops), so the same program drives real slabs over torch.distributed, several
 slabs on one GPU (tests) and a numpy stand-in under gloo on CPU (tests of the host logic).
@@ -56,6 +61,43 @@ def step_schedule(n_iterations: int, halo: int, pressure: bool, smoke: bool) -> 
     if smoke:
         ops.append(("advect_smoke",))
         ops.append(("exchange", F_SMOKE))
+    return ops
+
+
+def lazy_schedule(n_iterations: int, halo: int, pressure: bool, smoke: bool, margin: int = 16) -> List[tuple]:
+    """The schedule the library runs for linked slabs (csrc/sayal_api.cu step_impl), as data.
+
+    Ghost rows are exact to depth D beyond the owned rows.  An SOR iteration costs two rows of depth; an exchange
+    restores D = halo.  Exchanges happen only when the next operation needs more depth than is left:
+      * before an iteration when D < 2,
+      * before the velocity advection when D < margin + 1 (it runs on the owned rows and ONE ghost row each side
+        — the smoke sampler reads the new velocity one row away — and gathers from up to `margin` rows away),
+    and once at the end of the step for u, v and smoke together.  With halo >= 2 n + margin + 1 that is the only
+    exchange of the step."""
+    if halo < margin + 1 or halo < 2:
+        raise ValueError("halo must be >= margin + 1")
+    ops: List[tuple] = [("forces",)]
+    if pressure:
+        ops.append(("zero_pressure",))
+    depth, done = halo, 0
+    while done < n_iterations:
+        if depth < 2:
+            ops.append(("exchange", F_U | F_V))
+            depth = halo
+        k = min(n_iterations - done, depth // 2)
+        ops.append(("projection", k))
+        depth -= 2 * k
+        done += k
+    if pressure:
+        ops.append(("pressure_range",))
+    ops.append(("extrapolation",))
+    if depth < margin + 1:
+        ops.append(("exchange", F_U | F_V))
+        depth = halo
+    ops.append(("advect_velocity", 1))  # owned rows +- 1 ghost row
+    if smoke:
+        ops.append(("advect_smoke",))
+    ops.append(("exchange", F_U | F_V | (F_SMOKE if smoke else 0)))
     return ops
 
 
@@ -219,7 +261,8 @@ class SlabFluid:
     kernels on the sim's stream (csrc/slab_exchange.cu) and the whole step is one CUDA-graph replay per rank.
     transport "nccl": the same schedule driven from here, edge rows packed and sent with NCCL send/recv."""
 
-    def __init__(self, cfg, rank: int, world: int, device: int, halo: int = 16, group=None, transport: str = "p2p"):
+    def __init__(self, cfg, rank: int, world: int, device: int, halo: int = 16, group=None, transport: str = "p2p",
+                 margin: int = 16):
         self.cfg, self.rank, self.world, self.group = cfg, rank, world, group
         self.transport = transport if world > 1 else "none"
         c = cfg.c
@@ -231,6 +274,7 @@ class SlabFluid:
         self.ops = step_schedule(c.proj_n, halo, bool(c.enable_pressure), bool(c.enable_smoke) and c.wt_smoke != 0) \
             if world > 1 else None
         if self.transport == "p2p":
+            self.sim.set_option("advect_margin", margin)  # rows the advection may gather from (see lazy_schedule)
             link_dist(self.sim, rank, world, group)
             self.sim.run(0)  # choose the projection tile plans (may time candidates) before the first exchange
 
@@ -300,10 +344,22 @@ def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSa
         raise SystemExit("bench.py --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local)
     if not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout: keep stdout for the one JSON line
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     cfg = workload_config(world)
     c = cfg.c
-    halo = int(os.environ.get("SAYAL_SLAB_HALO", "32"))
+    margin = int(os.environ.get("SAYAL_ADVECT_MARGIN", "16"))
+    # deep halo: 2 n + margin + 1 ghost rows keep the owned rows exact through a whole step, so the step needs ONE
+    # exchange (hidden behind the interior smoke advection); thin slabs fall back to exchanging every halo/2 iterations
+    rows_per_rank = c.height // world
+    halo = int(os.environ.get("SAYAL_SLAB_HALO", "0")) or min(2 * c.proj_n + margin + 2, max(margin + 2, rows_per_rank // 4))
     transport = os.environ.get("SAYAL_SLAB_TRANSPORT", "p2p")
     sf = SlabFluid(cfg, rank, world, local, halo=halo, transport=transport)
     u, v, sm = synthetic_fields(c.width, c.height, rows=(sf.row0, sf.rows))

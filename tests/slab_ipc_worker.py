@@ -23,7 +23,7 @@ def main():
     cfg["sim.projection.n"] = 20
     cfg["sim.wind_tunnel.speed"] = 60.0
     c = cfg.c
-    sf = SlabFluid(cfg, rank, world, device, halo=16, transport="p2p")
+    sf = SlabFluid(cfg, rank, world, device, halo=16, transport="p2p", margin=6)
     u, v, sm = synthetic_fields(c.width, c.height, rows=(sf.row0, sf.rows))
     sf.set_initial(u, v, sm)
     sf.run(2)          # graph replays

@@ -55,10 +55,13 @@ class NumpySlab:
         elif kind in ("advect_velocity", "advect_smoke"):
             names = ("u", "v") if kind == "advect_velocity" else ("smoke",)
             own0 = self.row0 - self.lo
+            ghost = op[1] if len(op) > 1 else 0  # lazy schedule: also advect `ghost` rows beyond the owned ones
+            first = max(own0 - ghost, 0)
+            last = min(own0 + self.rows + ghost, len(self.f["u"]))
             for name in names:
                 a = self.f[name]
-                new = a.copy()
-                for lr in range(own0, own0 + self.rows):  # owned rows only
+                new = np.full_like(a, np.nan)  # rows that are not advected go stale, like the back buffer
+                for lr in range(first, last):
                     r = self.lo + lr
                     for i in range(W):
                         src = min(max(r + (i % (2 * REACH + 1)) - REACH, 0), H - 1)
@@ -99,7 +102,8 @@ def initial():
 
 def single_domain(steps):
     s = NumpySlab(initial(), 0, H, 0, True, True)
-    ops = [op for op in S.step_schedule(N_ITER, 8, False, True) if op[0] != "exchange"]
+    ops = [op[:1] + op[1:] if op[0] != "advect_velocity" else ("advect_velocity",)
+           for op in S.step_schedule(N_ITER, 8, False, True) if op[0] != "exchange"]
     for _ in range(steps):
         for op in ops:
             s.apply(op)
@@ -144,6 +148,53 @@ def test_local_exchange_matches_single_domain(world, halo):
     for s in slabs:
         for name in ("u", "v", "smoke"):
             assert np.array_equal(s.owned(name), want[name][s.row0:s.row0 + s.rows]), (name, s.row0)
+
+
+@pytest.mark.parametrize("world,halo", [(2, 4), (2, 6), (3, 9), (2, 18), (4, 5)])
+def test_lazy_schedule_matches_single_domain(world, halo):
+    """The schedule the library runs natively (exchanges only when the ghost depth runs out + one at the end of the
+    step).  halo 18 >= 2*7 + 3 + 1: a single exchange per step."""
+    full = initial()
+    slabs = []
+    for r in range(world):
+        row0, rows = S.slab_rows(H, world, r)
+        slabs.append(NumpySlab(full, row0, rows, halo, r == 0, r == world - 1))
+    ops = S.lazy_schedule(N_ITER, halo, False, True, margin=REACH)
+    if halo == 18:
+        assert sum(op[0] == "exchange" for op in ops) == 1
+    for _ in range(3):
+        S.run_schedule_local(slabs, ops)
+    want = single_domain(3)
+    for s in slabs:
+        for name in ("u", "v", "smoke"):
+            assert np.array_equal(s.owned(name), want[name][s.row0:s.row0 + s.rows]), (name, s.row0)
+
+
+def test_lazy_schedule_shape():
+    ops = S.lazy_schedule(50, 120, False, True)
+    assert [op[0] for op in ops] == ["forces", "projection", "extrapolation", "advect_velocity", "advect_smoke", "exchange"]
+    assert ops[-1] == ("exchange", S.F_U | S.F_V | S.F_SMOKE) and ops[1] == ("projection", 50)
+    ops = S.lazy_schedule(50, 32, True, False)
+    proj = [op[1] for op in ops if op[0] == "projection"]
+    assert proj == [16, 16, 16, 2] and sum(op[0] == "exchange" for op in ops) == 4  # 3 inside + 1 at the end
+    assert ops[-1] == ("exchange", S.F_U | S.F_V)
+    ops = S.lazy_schedule(7, 16, False, True, margin=3)  # depth left after 7 iterations: 2 < margin + 1
+    assert [op[0] for op in ops].count("exchange") == 2
+    with pytest.raises(ValueError):
+        S.lazy_schedule(4, 8, False, False, margin=16)
+
+
+def test_lazy_schedule_with_too_small_margin_is_detected():
+    """The stand-in gathers from REACH rows away: a schedule built for margin 1 must trip its assertion."""
+    full = initial()
+    slabs = []
+    for r in range(2):
+        row0, rows = S.slab_rows(H, 2, r)
+        slabs.append(NumpySlab(full, row0, rows, 8, r == 0, r == 1))
+    ops = S.lazy_schedule(N_ITER, 8, False, True, margin=1)
+    S.run_schedule_local(slabs, ops)
+    want = single_domain(1)
+    assert any(not np.array_equal(s.owned(n), want[n][s.row0:s.row0 + s.rows]) for s in slabs for n in ("u", "v"))
 
 
 def test_too_thin_halo_is_detected_by_this_test_design():

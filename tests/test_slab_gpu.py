@@ -95,16 +95,17 @@ def test_halo_overflow_is_reported():
 
 
 # ---- native transport: peer-memory exchange + whole-step graph (csrc/slab_exchange.cu) ---------------------
-def run_slabs_native(cfg, world, halo, steps, graph):
+def run_slabs_native(cfg, world, halo, steps, graph, margin=6, amplitude=40.0):
     """Slabs of one process on one device, linked with sayal_slab_connect_local; every slab runs the library's
     own slab schedule (sayal_step / sayal_run) and the exchange kernels talk through device memory."""
     from opensayal_b200 import Fluid as F
     c = cfg.c
-    u, v, sm = synthetic_fields(c.width, c.height)
+    u, v, sm = synthetic_fields(c.width, c.height, amplitude=amplitude)
     sims = []
     for r in range(world):
         row0, rows = S.slab_rows(c.height, world, r)
         f = F(cfg, device=0, slab=(row0, rows, halo))
+        f.set_option("advect_margin", margin)  # back-traces: 60 * 0.05 = 3 cells (+ 2.25 synthetic) + stencil
         f.set_field("u", u[row0:row0 + rows])
         f.set_field("v", v[row0:row0 + rows])
         f.set_field("smoke", sm[row0:row0 + rows])
@@ -135,9 +136,10 @@ def run_slabs_native(cfg, world, halo, steps, graph):
     return out, overflow, errors
 
 
-@pytest.mark.parametrize("world,halo", [(2, 16), (3, 12), (4, 32)])
+@pytest.mark.parametrize("world,halo", [(2, 16), (3, 12), (4, 32), (2, 47), (3, 60)])
 @pytest.mark.parametrize("graph", [0, 1])
 def test_native_linked_slabs_bit_identical_to_single_gpu(world, halo, graph):
+    """halo 47 = 2 * 20 + 6 + 1 and above: a single exchange per step (hidden behind the smoke advection)."""
     cfg = baseline_config(1, width=384, height=420)
     cfg["sim.projection.n"] = 20
     cfg["sim.wind_tunnel.speed"] = 60.0
@@ -161,6 +163,15 @@ def test_native_slabs_tall_domain_split_last_pass(overlap, monkeypatch):
     assert errors == 0 and overflow == 0
     for n in ("u", "v", "smoke"):
         assert np.array_equal(got[n], want[n]), n
+
+
+def test_native_slabs_report_a_too_small_margin():
+    """Fast flow (20-cell back-traces) with advect_margin 6: gathers leave the rows known to be exact -> counted."""
+    cfg = baseline_config(1, width=256, height=510)
+    cfg["sim.projection.n"] = 4
+    # three slabs: the synthetic v has a node at H/2, not at H/3
+    _, overflow, errors = run_slabs_native(cfg, 3, 24, 1, graph=0, margin=6, amplitude=400.0)
+    assert errors == 0 and overflow > 0
 
 
 def test_unlinked_slab_refuses_to_step():

@@ -18,7 +18,7 @@ dist.barrier()
 os.dup2(fd, 1)
 W = int(arg("--width", "1920")); rows = int(arg("--rows-per-gpu", "1080")); n = int(arg("--n", "50"))
 H = rows * world
-for halo in [int(x) for x in arg("--halos", "16,20,32,50").split(",")]:
+for halo in [int(x) for x in arg("--halos", "32,50,118").split(",")]:
     cfg = baseline_config(1, width=W, height=H)
     cfg["sim.projection.n"] = n
     cfg["sim.wind_tunnel.pipe_height"] = H // 4
