@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SAYAL_ABI_VERSION 1
+#define SAYAL_ABI_VERSION 2
 
 /* error codes */
 #define SAYAL_OK 0
@@ -32,6 +32,7 @@ extern "C" {
 #define SAYAL_EIO (-3)      /* config file missing / unreadable */
 #define SAYAL_EPARSE (-4)   /* config file is not valid JSON / wrong value type */
 #define SAYAL_ENOMEM (-5)
+#define SAYAL_EBUSY (-6)    /* frame ring full: acquire a frame first */
 
 /* fields, for sayal_get_field / sayal_set_field / sayal_device_ptr */
 enum sayal_field {
@@ -160,6 +161,72 @@ int sayal_stage_projection(sayal_sim* sim, int32_t iterations, float d_t);
 int sayal_stage_extrapolation(sayal_sim* sim);
 int sayal_stage_advect_velocity(sayal_sim* sim, float d_t);
 int sayal_stage_advect_smoke(sayal_sim* sim, float d_t);
+
+/* ---- diffusion (fluid.cu:167-190) ------------------------------------------------------------ */
+/* `iterations` sweeps of  u = (u + a (uW + uE + uS + uN)) / (1 + 4a),  a = viscosity d_t / cell_size^2, over the
+ * interior cells, u only — the reference's apply_diffusion, which Fluid::update runs n times when
+ * fluid.viscosity != 0 (fluid.cu:775-777).  The reference sweeps in place in whatever order the blocks happen
+ * to run (a data race); here the order is fixed: cells with (i+j) even, then (i+j) odd.  The two differ by
+ * O(a^2) per sweep (a = 5e-5 with the shipped defaults), far inside the 1e-5 parity tolerance.
+ * sayal_step / sayal_run run this stage between the forces and the projection when viscosity != 0. */
+int sayal_stage_diffusion(sayal_sim* sim, int32_t iterations, float d_t);
+
+/* ---- the renderer's consumers of the state (graphics_handler.cu) ------------------------------------------
+ * Everything GraphicsHandler::update (graphics_handler.cu:463-478) computes from the Fluid, without SDL: the
+ * RGBA8888 frame, the velocity arrows and the path lines.  A headless caller (sayal_run --frames) or a patched
+ * main.cu draws / stores them; stepping never waits for the read-back unless the caller asks for the result. */
+
+/* The members of `Config` GraphicsHandler reads (graphics_handler.cu:99-121; defaults config_parser.cpp:40,120-181). */
+typedef struct sayal_visual {
+  int32_t cell_pixel_size;         /* sim.cell_pixel_size          (1)  */
+  int32_t arrows_enable;           /* visual.arrows.enable         (false) */
+  int32_t arrows_distance;         /* visual.arrows.distance       (20) */
+  float arrows_length_multiplier;  /* visual.arrows.length_multiplier (0.1) */
+  float arrows_disable_threshold;  /* visual.arrows.disable_threshold (0) */
+  int32_t arrows_head_length;      /* visual.arrows.head_length    (5)  */
+  int32_t path_line_enable;        /* visual.path_line.enable      (false) */
+  int32_t path_line_length;        /* visual.path_line.length      (20) */
+  int32_t path_line_distance;      /* visual.path_line.distance    (20) */
+  int32_t arrows_color[4];         /* visual.arrows.color.{r,g,b,a}    (0,0,0,255) — carried for the caller */
+  int32_t path_line_color[4];      /* visual.path_line.color.{r,g,b,a} (0,0,0,255) */
+} sayal_visual;
+int sayal_visual_defaults(sayal_visual* v);
+int sayal_visual_load(const char* json_path, sayal_visual* v);
+int sayal_visual_parse(const char* json_text, size_t len, sayal_visual* v);
+
+/* struct ArrowData (graphics_handler.cuh:17-27), pixel coordinates; `valid` 0 for solid cells and for
+ * arrows shorter than the threshold (the reference leaves those entries untouched / stale). */
+typedef struct sayal_arrow {
+  int32_t start_x, start_y, end_x, end_y;
+  int32_t right_head_end_x, right_head_end_y, left_head_end_x, left_head_end_y;
+  int32_t valid;
+} sayal_arrow;
+
+/* update_fluid_pixels_kernel + the copy to the host (graphics_handler.cu:258-302): one uint32 per cell,
+ * r<<24 | g<<16 | b<<8 | a, pixel (x = i, y = H-1-j) at y*W + x — the layout of the fields.  Solid cells are
+ * (80,80,80); smoke only: (255, c, c) with c = 255 - uint8(smoke*255); with pressure: HSV hue from the pressure
+ * normalised by the last step's min / max (read on the device, no host round trip), value from smoke.
+ * Synchronous; a slab sim writes its owned rows. */
+int sayal_render_pixels(sayal_sim* sim, uint32_t* host_dst);
+/* The same frame without stalling the step stream: submit renders the state as of the work enqueued so far into
+ * one of three device buffers and copies it to pinned host memory on a second stream; stepping may continue at
+ * once.  acquire waits for the OLDEST submitted frame only and returns the library-owned pinned buffer plus the
+ * number of updates it shows; the buffer stays valid until the second submit after the acquire.  At most two
+ * frames may be outstanding: a third submit returns SAYAL_EBUSY.  Cells the reference leaves untouched (neither
+ * smoke nor pressure enabled) read 0. */
+int sayal_frame_submit(sayal_sim* sim);
+int sayal_frame_acquire(sayal_sim* sim, const uint32_t** pixels, int64_t* step_index);
+/* update_center_velocity_arrow (graphics_handler.cu:304-356) + make_arrow_data (:168-200): one arrow per
+ * arrows_distance cells, (W / distance) x (H / distance) entries, entry (a, b) — cell (a*distance, b*distance) —
+ * at (n_y - 1 - b) * n_x + a (indx_arrow_data, :12-14).  host_dst holds `capacity` entries. */
+int sayal_arrows(sayal_sim* sim, const sayal_visual* v, sayal_arrow* host_dst, int32_t capacity, int32_t* n_x,
+                 int32_t* n_y);
+/* update_traces (graphics_handler.cu:358-421) over Fluid::trace (fluid.cu:16-36): from the centre of every
+ * path_line_distance-th cell, `length` points of forward Euler through get_general_velocity with step d_t, as
+ * rounded pixel coordinates (x, H-1-y).  Line (a, b) occupies [((n_y-1-b) * n_x + a) * length, +length) of host_x /
+ * host_y (indx_traces, :8-11); lines starting in a solid cell are all -1. */
+int sayal_path_lines(sayal_sim* sim, const sayal_visual* v, float d_t, int32_t* host_x, int32_t* host_y,
+                     int32_t capacity, int32_t* n_x, int32_t* n_y);
 
 /* Tuning / introspection.  set: "projection_kernel" (0 = plain half-sweeps, 1 = register-tile temporally
  * blocked), "temporal_block" (iterations per pass, 0 = choose), "tile_rows_per_warp" (0 = choose, 8/10/12),

@@ -4,6 +4,6 @@ The package holds only what the path needs: csrc/ (CUDA kernels + the C ABI of i
 ctypes mirror of the reference's `ConfigParser` / `Source` / `Fluid` interface.
 """
 from ._abi import LIB_PATH, SayalError, load  # noqa: F401
-from .fluid import Config, ConfigParser, Fluid, Source  # noqa: F401
+from .fluid import Config, ConfigParser, Fluid, Source, Visual  # noqa: F401
 
-__all__ = ["Config", "ConfigParser", "Fluid", "Source", "SayalError", "load", "LIB_PATH"]
+__all__ = ["Config", "ConfigParser", "Fluid", "Source", "Visual", "SayalError", "load", "LIB_PATH"]

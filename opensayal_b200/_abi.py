@@ -83,11 +83,49 @@ class SayalSlab(C.Structure):
     ]
 
 
+class SayalVisual(C.Structure):
+    """struct sayal_visual — the members of Config GraphicsHandler reads (graphics_handler.cu:99-121)."""
+
+    _fields_ = [
+        ("cell_pixel_size", C.c_int32),
+        ("arrows_enable", C.c_int32),
+        ("arrows_distance", C.c_int32),
+        ("arrows_length_multiplier", C.c_float),
+        ("arrows_disable_threshold", C.c_float),
+        ("arrows_head_length", C.c_int32),
+        ("path_line_enable", C.c_int32),
+        ("path_line_length", C.c_int32),
+        ("path_line_distance", C.c_int32),
+        ("arrows_color", C.c_int32 * 4),
+        ("path_line_color", C.c_int32 * 4),
+    ]
+
+
+class SayalArrow(C.Structure):
+    """struct sayal_arrow == ArrowData (graphics_handler.cuh:17-27) with an int32 `valid`."""
+
+    _fields_ = [(n, C.c_int32) for n in ("start_x", "start_y", "end_x", "end_y", "right_head_end_x", "right_head_end_y",
+                                         "left_head_end_x", "left_head_end_y", "valid")]
+
+
+ARROW_DTYPE = [(n, "<i4") for n, _ in SayalArrow._fields_]
+
 # every symbol include/sayal.h declares: (name, restype, argtypes)
 _cfgp = C.POINTER(SayalConfig)
 _srcp = C.POINTER(SayalSource)
 _simp = C.c_void_p
+_visp = C.POINTER(SayalVisual)
+_i32p = C.POINTER(C.c_int32)
 SYMBOLS = [
+    ("sayal_visual_defaults", C.c_int, [_visp]),
+    ("sayal_visual_load", C.c_int, [C.c_char_p, _visp]),
+    ("sayal_visual_parse", C.c_int, [C.c_char_p, C.c_size_t, _visp]),
+    ("sayal_stage_diffusion", C.c_int, [_simp, C.c_int32, C.c_float]),
+    ("sayal_render_pixels", C.c_int, [_simp, C.c_void_p]),
+    ("sayal_frame_submit", C.c_int, [_simp]),
+    ("sayal_frame_acquire", C.c_int, [_simp, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    ("sayal_arrows", C.c_int, [_simp, _visp, C.c_void_p, C.c_int32, _i32p, _i32p]),
+    ("sayal_path_lines", C.c_int, [_simp, _visp, C.c_float, C.c_void_p, C.c_void_p, C.c_int32, _i32p, _i32p]),
     ("sayal_config_defaults", C.c_int, [C.c_int32, C.c_int32, _cfgp]),
     ("sayal_config_load", C.c_int, [C.c_char_p, _cfgp]),
     ("sayal_config_parse", C.c_int, [C.c_char_p, C.c_size_t, _cfgp]),
@@ -124,6 +162,7 @@ SYMBOLS = [
     ("sayal_abi_version", C.c_int, []),
 ]
 
+ABI_VERSION = 2
 _lib = None
 
 
@@ -148,7 +187,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header and library disagree
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.sayal_abi_version() != 1:
+    if lib.sayal_abi_version() != ABI_VERSION:
         raise ImportError("libsayal_b200.so: ABI version mismatch")
     _lib = lib
     return lib

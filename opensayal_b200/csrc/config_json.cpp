@@ -297,3 +297,68 @@ extern "C" int sayal_config_load(const char* path, sayal_config* c) {
   fclose(f);
   return sayal_config_parse(text.data(), text.size(), c);
 }
+
+// ---- the renderer's subset of Config (config_parser.cpp:40, 120-181) ------------------------------------------
+extern "C" int sayal_visual_defaults(sayal_visual* v) {
+  if (!v) return sayal::set_error(SAYAL_EINVAL, "sayal_visual_defaults: null argument");
+  std::memset(v, 0, sizeof(*v));
+  v->cell_pixel_size = 1;
+  v->arrows_enable = 0;
+  v->arrows_distance = 20;
+  v->arrows_length_multiplier = 0.1f;
+  v->arrows_disable_threshold = 0.0f;
+  v->arrows_head_length = 5;
+  v->path_line_enable = 0;
+  v->path_line_length = 20;
+  v->path_line_distance = 20;
+  v->arrows_color[3] = 255;
+  v->path_line_color[3] = 255;
+  return SAYAL_OK;
+}
+
+extern "C" int sayal_visual_parse(const char* text, size_t len, sayal_visual* v) {
+  if (!text || !v) return sayal::set_error(SAYAL_EINVAL, "sayal_visual_parse: null argument");
+  Parser ps{text, text + len, {}};
+  JValue root;
+  if (!ps.parse_value(root, 0)) return sayal::set_error(SAYAL_EPARSE, ("config: " + ps.err).c_str());
+  ps.ws();
+  if (ps.p != ps.end) return sayal::set_error(SAYAL_EPARSE, "config: trailing characters after JSON value");
+  sayal_visual_defaults(v);
+  bool fatal = false;
+#define VGET(key, field) get_or(root, key, &v->field, true, &fatal)
+#define VGET_B(key, field)                                  \
+  do {                                                      \
+    BoolT t{v->field};                                      \
+    if (get_or(root, key, &t, true, &fatal)) v->field = t.v; \
+  } while (0)
+  VGET("sim.cell_pixel_size", cell_pixel_size);
+  VGET_B("visual.arrows.enable", arrows_enable);
+  VGET("visual.arrows.distance", arrows_distance);
+  VGET("visual.arrows.length_multiplier", arrows_length_multiplier);
+  VGET("visual.arrows.disable_threshold", arrows_disable_threshold);
+  VGET("visual.arrows.head_length", arrows_head_length);
+  VGET_B("visual.path_line.enable", path_line_enable);
+  VGET("visual.path_line.length", path_line_length);
+  VGET("visual.path_line.distance", path_line_distance);
+  static const char* rgba[4] = {"r", "g", "b", "a"};
+  for (int k = 0; k < 4; k++) {
+    get_or(root, std::string("visual.arrows.color.") + rgba[k], &v->arrows_color[k], true, &fatal);
+    get_or(root, std::string("visual.path_line.color.") + rgba[k], &v->path_line_color[k], true, &fatal);
+  }
+#undef VGET
+#undef VGET_B
+  if (fatal) return sayal::set_error(SAYAL_EPARSE, "config: a top-level key holds a value of the wrong type");
+  return SAYAL_OK;
+}
+
+extern "C" int sayal_visual_load(const char* path, sayal_visual* v) {
+  if (!path || !v) return sayal::set_error(SAYAL_EINVAL, "sayal_visual_load: null argument");
+  FILE* f = fopen(path, "rb");
+  if (!f) return sayal::set_error(SAYAL_EIO, (std::string("cannot open config file ") + path).c_str());
+  std::string text;
+  char buf[65536];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, n);
+  fclose(f);
+  return sayal_visual_parse(text.data(), text.size(), v);
+}

@@ -54,6 +54,13 @@ static void free_sim(Sim* s) {
     if (s->ipc_opened[k]) cudaIpcCloseMemHandle(s->ipc_opened[k]);
   if (s->link_block) cudaFree(s->link_block);
   if (s->link_counters) cudaFree(s->link_counters);
+  for (int k = 0; k < Sim::kFrames; k++) {
+    if (s->d_frame[k]) cudaFree(s->d_frame[k]);
+    if (s->h_frame[k]) cudaFreeHost(s->h_frame[k]);
+    if (s->ev_rendered[k]) cudaEventDestroy(s->ev_rendered[k]);
+    if (s->ev_copied[k]) cudaEventDestroy(s->ev_copied[k]);
+  }
+  if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
   if (s->ev_fork) cudaEventDestroy(s->ev_fork);
   if (s->ev_join) cudaEventDestroy(s->ev_join);
   if (s->aux_stream) cudaStreamDestroy(s->aux_stream);
@@ -182,6 +189,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   cudaMemsetAsync(s->flags, FL_SOLID, field_elems(s) + 64, s->stream);
   e = cudaMalloc(&s->d_range, 2 * sizeof(int32_t));
   if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
+  cudaMemsetAsync(s->d_range, 0, 2 * sizeof(int32_t), s->stream);  // min = max = 0 until the first step (fluid.cuh:61-62 are uninitialised there)
   e = cudaMalloc(&s->d_overflow, sizeof(int32_t));
   if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
   cudaMemsetAsync(s->d_overflow, 0, sizeof(int32_t), s->stream);
@@ -288,7 +296,21 @@ static int step_impl(Sim* s, const sayal_source* src, float d_t) {
   const bool linked = is_linked(s);
   TRY(launch_forces(s, src, d_t));
   if (s->ph.enable_pressure) TRY(launch_zero_pressure(s));
-  // viscosity: the reference's racy diffusion loop (fluid.cu:185-190, H1) is out of scope; see DESIGN.md
+  // apply_diffusion (fluid.cu:775-777): n sweeps over u when viscosity != 0, in a fixed red-black order (H1).
+  // A sweep has the same one-row dependency radius per colour as a projection half-sweep, so linked slabs chunk it
+  // the same way: halo/2 sweeps, then an exchange of u.
+  if (s->cfg.viscosity != 0.f) {
+    if (!linked) {
+      TRY(launch_diffusion(s, s->cfg.proj_n, d_t));
+    } else {
+      for (int done = 0; done < s->cfg.proj_n;) {
+        int k = s->cfg.proj_n - done < s->slab_halo / 2 ? s->cfg.proj_n - done : s->slab_halo / 2;
+        TRY(launch_diffusion(s, k, d_t));
+        TRY(launch_slab_exchange(s, 1));
+        done += k;
+      }
+    }
+  }
   // y-slab (linked): ghost rows are exact to depth D beyond the owned rows; every SOR iteration costs two rows
   // of depth, an exchange restores D = halo.  Exchanges happen only when the next operation needs more depth
   // than is left, and once at the end of the step (u, v and smoke together).
@@ -374,6 +396,7 @@ int sayal_step(sayal_sim* sim, const sayal_source* src, float d_t) {
   if (is_slab(s) && !is_linked(s)) return set_error(SAYAL_EINVAL, "sayal_step: a slab sim must be linked to its neighbours first (sayal_slab_ipc_connect / sayal_slab_connect_local), or stepped stage by stage");
   if (is_linked(s) && s->slab_halo < s->advect_margin + 1) return set_error(SAYAL_EINVAL, "sayal_step: linked slabs need halo >= advect_margin + 1 (default 17)");
   CUDA_TRY(cudaSetDevice(s->device));
+  s->steps_done++;
   return step_impl(s, src, d_t);
 }
 
@@ -431,9 +454,13 @@ int sayal_run(sayal_sim* sim, int32_t steps, float d_t) {
     s->smoke = ps.smoke; s->smoke_buf = ps.smoke_buf; s->parity = ps.parity;
     s->launches += s->graph_launches[slot];
     if (s->ph.enable_pressure) s->range_valid = false;
+    s->steps_done++;
     remaining--;
   }
-  for (; remaining > 0; remaining--) TRY(step_impl(s, nullptr, d_t));
+  for (; remaining > 0; remaining--) {
+    s->steps_done++;
+    TRY(step_impl(s, nullptr, d_t));
+  }
   return SAYAL_OK;
 }
 
@@ -596,6 +623,124 @@ int sayal_stage_advect_velocity(sayal_sim* sim, float d_t) {
 int sayal_stage_advect_smoke(sayal_sim* sim, float d_t) {
   STAGE_PROLOGUE("sayal_stage_advect_smoke");
   return advect_smoke(s, d_t);
+}
+
+int sayal_stage_diffusion(sayal_sim* sim, int32_t iterations, float d_t) {
+  STAGE_PROLOGUE("sayal_stage_diffusion");
+  if (iterations < 0) return set_error(SAYAL_EINVAL, "sayal_stage_diffusion: iterations < 0");
+  return launch_diffusion(s, iterations, d_t);
+}
+
+// ---- renderer-side consumers (visual.cu) --------------------------------------------------------------
+static size_t frame_pixels(const Sim* s) { return (size_t)s->g.W * (s->g.own_hi - s->g.own_lo); }
+
+static int frame_ring_init(Sim* s) {
+  if (s->copy_stream) return SAYAL_OK;
+  CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < Sim::kFrames; k++) {
+    CUDA_TRY(cudaMalloc(&s->d_frame[k], frame_pixels(s) * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemsetAsync(s->d_frame[k], 0, frame_pixels(s) * sizeof(uint32_t), s->stream));
+    CUDA_TRY(cudaHostAlloc(&s->h_frame[k], frame_pixels(s) * sizeof(uint32_t), cudaHostAllocDefault));
+    CUDA_TRY(cudaEventCreateWithFlags(&s->ev_rendered[k], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s->ev_copied[k], cudaEventDisableTiming));
+  }
+  return SAYAL_OK;
+}
+
+int sayal_frame_submit(sayal_sim* sim) {
+  STAGE_PROLOGUE("sayal_frame_submit");
+  TRY(frame_ring_init(s));
+  if (s->frame_pending >= 2) return set_error(SAYAL_EBUSY, "sayal_frame_submit: two frames outstanding, acquire one first");
+  const int k = s->frame_head;
+  // the device frame may still be the source of the copy submitted three frames ago
+  if (s->frame_used[k]) CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_copied[k], 0));
+  TRY(launch_render_pixels(s, s->d_frame[k]));
+  CUDA_TRY(cudaEventRecord(s->ev_rendered[k], s->stream));
+  CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->ev_rendered[k], 0));
+  CUDA_TRY(cudaMemcpyAsync(s->h_frame[k], s->d_frame[k], frame_pixels(s) * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                           s->copy_stream));
+  CUDA_TRY(cudaEventRecord(s->ev_copied[k], s->copy_stream));
+  s->frame_used[k] = true;
+  s->frame_step[k] = s->steps_done;
+  s->frame_head = (s->frame_head + 1) % Sim::kFrames;
+  s->frame_pending++;
+  return SAYAL_OK;
+}
+
+int sayal_frame_acquire(sayal_sim* sim, const uint32_t** pixels, int64_t* step_index) {
+  STAGE_PROLOGUE("sayal_frame_acquire");
+  if (!pixels) return set_error(SAYAL_EINVAL, "sayal_frame_acquire: null argument");
+  if (s->frame_pending <= 0) return set_error(SAYAL_EINVAL, "sayal_frame_acquire: no frame was submitted");
+  const int k = (s->frame_head + Sim::kFrames - s->frame_pending) % Sim::kFrames;  // the oldest outstanding slot
+  CUDA_TRY(cudaEventSynchronize(s->ev_copied[k]));
+  *pixels = s->h_frame[k];
+  if (step_index) *step_index = s->frame_step[k];
+  s->frame_pending--;
+  return SAYAL_OK;
+}
+
+int sayal_render_pixels(sayal_sim* sim, uint32_t* host_dst) {
+  STAGE_PROLOGUE("sayal_render_pixels");
+  if (!host_dst) return set_error(SAYAL_EINVAL, "sayal_render_pixels: null destination");
+  uint32_t* d = nullptr;
+  const size_t bytes = frame_pixels(s) * sizeof(uint32_t);
+  CUDA_TRY(cudaMalloc(&d, bytes));
+  // cells the reference leaves untouched (neither smoke nor pressure enabled) keep the caller's pixels
+  cudaMemcpyAsync(d, host_dst, bytes, cudaMemcpyHostToDevice, s->stream);
+  int r = launch_render_pixels(s, d);
+  if (r == SAYAL_OK) cudaMemcpyAsync(host_dst, d, bytes, cudaMemcpyDeviceToHost, s->stream);
+  cudaError_t e = cudaStreamSynchronize(s->stream);
+  cudaFree(d);
+  if (r != SAYAL_OK) return r;
+  if (e != cudaSuccess) return set_error(SAYAL_ECUDA, cudaGetErrorString(e));
+  return SAYAL_OK;
+}
+
+int sayal_arrows(sayal_sim* sim, const sayal_visual* v, sayal_arrow* host_dst, int32_t capacity, int32_t* n_x, int32_t* n_y) {
+  STAGE_PROLOGUE("sayal_arrows");
+  if (!v || v->arrows_distance < 1 || v->cell_pixel_size < 1) return set_error(SAYAL_EINVAL, "sayal_arrows: arrows.distance and cell_pixel_size must be >= 1");
+  const int nx = s->g.W / v->arrows_distance, ny = s->g.H / v->arrows_distance;
+  if (n_x) *n_x = nx;
+  if (n_y) *n_y = ny;
+  if (!host_dst) return SAYAL_OK;  // size query
+  if ((int64_t)capacity < (int64_t)nx * ny) return set_error(SAYAL_EINVAL, "sayal_arrows: destination too small");
+  if (nx * ny == 0) return SAYAL_OK;
+  sayal_arrow* d = nullptr;
+  const size_t bytes = sizeof(sayal_arrow) * (size_t)nx * ny;
+  CUDA_TRY(cudaMalloc(&d, bytes));
+  int r = launch_arrows(s, v, nx, ny, d);
+  if (r == SAYAL_OK) cudaMemcpyAsync(host_dst, d, bytes, cudaMemcpyDeviceToHost, s->stream);
+  cudaError_t e = cudaStreamSynchronize(s->stream);
+  cudaFree(d);
+  if (r != SAYAL_OK) return r;
+  if (e != cudaSuccess) return set_error(SAYAL_ECUDA, cudaGetErrorString(e));
+  return SAYAL_OK;
+}
+
+int sayal_path_lines(sayal_sim* sim, const sayal_visual* v, float d_t, int32_t* host_x, int32_t* host_y, int32_t capacity,
+                     int32_t* n_x, int32_t* n_y) {
+  STAGE_PROLOGUE("sayal_path_lines");
+  if (!v || v->path_line_distance < 1 || v->path_line_length < 1) return set_error(SAYAL_EINVAL, "sayal_path_lines: path_line.distance and .length must be >= 1");
+  const int nx = s->g.W / v->path_line_distance, ny = s->g.H / v->path_line_distance, len = v->path_line_length;
+  if (n_x) *n_x = nx;
+  if (n_y) *n_y = ny;
+  if (!host_x && !host_y) return SAYAL_OK;  // size query
+  if (!host_x || !host_y) return set_error(SAYAL_EINVAL, "sayal_path_lines: null destination");
+  const int64_t total = (int64_t)nx * ny * len;
+  if ((int64_t)capacity < total) return set_error(SAYAL_EINVAL, "sayal_path_lines: destination too small");
+  if (total == 0) return SAYAL_OK;
+  int32_t* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(int32_t) * 2 * (size_t)total));
+  int r = launch_path_lines(s, v->path_line_distance, len, d_t, nx, ny, d, d + total);
+  if (r == SAYAL_OK) {
+    cudaMemcpyAsync(host_x, d, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, s->stream);
+    cudaMemcpyAsync(host_y, d + total, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, s->stream);
+  }
+  cudaError_t e = cudaStreamSynchronize(s->stream);
+  cudaFree(d);
+  if (r != SAYAL_OK) return r;
+  if (e != cudaSuccess) return set_error(SAYAL_ECUDA, cudaGetErrorString(e));
+  return SAYAL_OK;
 }
 
 // ---- options --------------------------------------------------------------------------------------

@@ -114,6 +114,17 @@ struct Sim {
   cudaEvent_t ev_fork, ev_join;
   int overlap_exchange;     // option: overlap exchanges with interior compute (default 1)
   int advect_margin;        // ghost depth the advection may gather from: ceil(max|velocity| d_t) + 2 (default 16)
+  // frame read-back ring (visual.cu / sayal_frame_*): three device frames, three pinned host frames, a copy
+  // stream; at most two frames outstanding, so an acquired frame survives one further submit
+  static constexpr int kFrames = 3;
+  int64_t steps_done;       // updates enqueued since creation
+  uint32_t* d_frame[kFrames];
+  uint32_t* h_frame[kFrames];  // cudaHostAlloc
+  cudaEvent_t ev_rendered[kFrames], ev_copied[kFrames];
+  cudaStream_t copy_stream;
+  int64_t frame_step[kFrames];
+  int frame_head, frame_pending;  // next slot to submit into, frames submitted and not yet acquired
+  bool frame_used[kFrames];       // ev_copied[k] has been recorded at least once
 };
 
 // ---- kernels_basic.cu ---------------------------------------------------------------------------
@@ -140,6 +151,12 @@ int slab_link_connect(Sim* s, int side, void* peer_block, size_t peer_stage_elem
 size_t slab_link_stage_elems(const Sim* s);
 int launch_slab_exchange(Sim* s, int field_mask);
 int launch_slab_exchange_on(Sim* s, int field_mask, cudaStream_t stream);
+
+// ---- visual.cu -------------------------------------------------------------------------------------
+int launch_diffusion(Sim* s, int iterations, float d_t);
+int launch_render_pixels(Sim* s, uint32_t* d_pixels);  // owned rows, pitch W
+int launch_path_lines(Sim* s, int dist, int len, float d_t, int nx, int ny, int32_t* d_xs, int32_t* d_ys);
+int launch_arrows(Sim* s, const sayal_visual* v, int nx, int ny, sayal_arrow* d_out);
 
 // ---- projection_pack.cu --------------------------------------------------------------------------
 int launch_projection_tiled(Sim* s, int iterations, float d_t);

@@ -21,7 +21,7 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 
 from . import _abi
-from ._abi import SayalConfig, SayalSlab, SayalSource, check, load
+from ._abi import SayalConfig, SayalSlab, SayalSource, SayalVisual, check, load
 
 # JSON key of the reference -> member of sayal_config
 _KEYS = {
@@ -124,6 +124,32 @@ class ConfigParser:
         return Config(c)
 
 
+class Visual:
+    """The members of `Config` GraphicsHandler reads (graphics_handler.cu:99-121): sim.cell_pixel_size,
+    visual.arrows.*, visual.path_line.*; defaults of config_parser.cpp:40, 120-181."""
+
+    def __init__(self, v: Optional[SayalVisual] = None, **overrides):
+        if v is None:
+            v = SayalVisual()
+            check(load().sayal_visual_defaults(C.byref(v)))
+        self.v = v
+        for key, value in overrides.items():
+            setattr(self.v, key, value)
+
+    @staticmethod
+    def parse_text(text: str) -> "Visual":
+        v = SayalVisual()
+        raw = text.encode()
+        check(load().sayal_visual_parse(raw, len(raw), C.byref(v)))
+        return Visual(v)
+
+    @staticmethod
+    def parse_file(path: str) -> "Visual":
+        v = SayalVisual()
+        check(load().sayal_visual_load(str(path).encode(), C.byref(v)))
+        return Visual(v)
+
+
 @dataclass
 class Source:
     """struct Source (fluid.cuh:8-13); default = the inactive source a headless run passes."""
@@ -209,6 +235,9 @@ class Fluid:
     def stage_projection(self, iterations: int, d_t: float):
         check(self._lib.sayal_stage_projection(self._sim, iterations, d_t))
 
+    def stage_diffusion(self, iterations: int, d_t: float):
+        check(self._lib.sayal_stage_diffusion(self._sim, iterations, d_t))
+
     def stage_extrapolation(self):
         check(self._lib.sayal_stage_extrapolation(self._sim))
 
@@ -264,6 +293,47 @@ class Fluid:
                                               ys.ctypes.data_as(C.c_void_p), ou.ctypes.data_as(C.c_void_p),
                                               ov.ctypes.data_as(C.c_void_p)))
         return ou, ov
+
+    # ---- what GraphicsHandler::update computes from the fluid (graphics_handler.cu:463-478) ------------
+    def render_pixels(self, prefill: int = 0) -> np.ndarray:
+        """update_fluid_pixels: (rows, W) uint32 RGBA8888 frame of the current state, synchronous."""
+        out = np.full((self.rows, self.width), prefill, dtype=np.uint32)
+        check(self._lib.sayal_render_pixels(self._sim, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def frame_submit(self) -> None:
+        """Render the state as of the work enqueued so far and start its copy to pinned host memory; returns at once."""
+        check(self._lib.sayal_frame_submit(self._sim))
+
+    def frame_acquire(self, copy: bool = True):
+        """(frame, step index) of the oldest submitted frame; waits for that copy only."""
+        p, step = C.c_void_p(), C.c_int64()
+        check(self._lib.sayal_frame_acquire(self._sim, C.byref(p), C.byref(step)))
+        buf = (C.c_uint32 * (self.rows * self.width)).from_address(p.value)
+        a = np.ctypeslib.as_array(buf).reshape(self.rows, self.width)
+        return (a.copy() if copy else a), step.value
+
+    def arrows(self, visual: "Visual") -> np.ndarray:
+        """update_center_velocity_arrow: structured array (n_y, n_x) of ArrowData, row 0 = top of the picture."""
+        nx, ny = C.c_int32(), C.c_int32()
+        check(self._lib.sayal_arrows(self._sim, C.byref(visual.v), None, 0, C.byref(nx), C.byref(ny)))
+        out = np.zeros((ny.value, nx.value), dtype=_abi.ARROW_DTYPE)
+        if out.size:
+            check(self._lib.sayal_arrows(self._sim, C.byref(visual.v), out.ctypes.data_as(C.c_void_p), out.size,
+                                         C.byref(nx), C.byref(ny)))
+        return out
+
+    def path_lines(self, visual: "Visual", d_t: Optional[float] = None):
+        """update_traces: (xs, ys) int32 arrays of shape (n_y, n_x, length); lines from solid cells are -1."""
+        d_t = self.config.c.d_t if d_t is None else d_t
+        nx, ny = C.c_int32(), C.c_int32()
+        check(self._lib.sayal_path_lines(self._sim, C.byref(visual.v), d_t, None, None, 0, C.byref(nx), C.byref(ny)))
+        shape = (ny.value, nx.value, visual.v.path_line_length)
+        xs, ys = np.zeros(shape, np.int32), np.zeros(shape, np.int32)
+        if xs.size:
+            check(self._lib.sayal_path_lines(self._sim, C.byref(visual.v), d_t, xs.ctypes.data_as(C.c_void_p),
+                                             ys.ctypes.data_as(C.c_void_p), xs.size, C.byref(nx), C.byref(ny)))
+        return xs, ys
 
     # ---- tuning / introspection ----------------------------------------------------------------
     def set_option(self, key: str, value: int) -> None:

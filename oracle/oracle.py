@@ -10,7 +10,7 @@ from pathlib import Path
 
 import numpy as np
 
-from opensayal_b200._abi import FIELD_NAMES, IS_SOLID, TOTAL_S, SayalConfig, SayalSource
+from opensayal_b200._abi import ARROW_DTYPE, FIELD_NAMES, IS_SOLID, TOTAL_S, SayalConfig, SayalSource, SayalVisual
 
 HERE = Path(__file__).resolve().parent
 ORACLE_LIB = HERE / "liboracle.so"
@@ -45,6 +45,9 @@ def _load_oracle():
         "oracle_step": (None, [vp, srcp, C.c_float]),
         "oracle_sample_velocity": (None, [vp, C.c_int, vp, vp, vp, vp]),
         "oracle_render_pixels": (None, [vp, vp]),
+        "oracle_diffusion": (None, [vp, C.c_int, C.c_float]),
+        "oracle_path_lines": (None, [vp, C.POINTER(SayalVisual), C.c_float, vp, vp]),
+        "oracle_arrows": (None, [vp, C.POINTER(SayalVisual), vp]),
         "oracle_max_threads": (C.c_int, []),
     }
     for name, (res, args) in sig.items():
@@ -142,6 +145,24 @@ class OracleSim:
         self.lib.oracle_render_pixels(self.h, out.ctypes.data)
         return out
 
+    def diffusion(self, iterations, d_t):
+        self.lib.oracle_diffusion(self.h, iterations, d_t)
+
+    def path_lines(self, visual: SayalVisual, d_t=None):
+        """update_traces over Fluid::trace: (xs, ys), shape (n_y, n_x, length)."""
+        ny, nx = self.shape[0] // visual.path_line_distance, self.shape[1] // visual.path_line_distance
+        xs = np.zeros((ny, nx, visual.path_line_length), np.int32)
+        ys = np.zeros_like(xs)
+        self.lib.oracle_path_lines(self.h, C.byref(visual), self.cfg.d_t if d_t is None else d_t, xs.ctypes.data,
+                                   ys.ctypes.data)
+        return xs, ys
+
+    def arrows(self, visual: SayalVisual) -> np.ndarray:
+        ny, nx = self.shape[0] // visual.arrows_distance, self.shape[1] // visual.arrows_distance
+        out = np.zeros((ny, nx), dtype=ARROW_DTYPE)
+        self.lib.oracle_arrows(self.h, C.byref(visual), out.ctypes.data)
+        return out
+
     def sample_velocity(self, xs, ys):
         xs = np.ascontiguousarray(xs, np.float32)
         ys = np.ascontiguousarray(ys, np.float32)
@@ -208,3 +229,55 @@ class RefSim:
         mn, mx = C.c_float(), C.c_float()
         self.lib.ref_pressure_range(self.h, C.byref(mn), C.byref(mx))
         return mn.value, mx.value
+
+
+class RefGfx:
+    """The reference's own GraphicsHandler (graphics_handler.cu, unmodified) run headless over recording SDL stubs
+    (oracle/ref_shim.cu): update() is graphics.update(fluid, d_t) of main.cu:98; what it handed to SDL is returned."""
+
+    def __init__(self, ref: RefSim, visual: SayalVisual):
+        lib = ref.lib
+        vp = C.c_void_p
+        lib.ref_gfx_create.restype, lib.ref_gfx_create.argtypes = C.c_int, [C.POINTER(SayalConfig), C.POINTER(SayalVisual), C.POINTER(vp)]
+        lib.ref_gfx_destroy.restype, lib.ref_gfx_destroy.argtypes = None, [vp]
+        lib.ref_gfx_update.restype, lib.ref_gfx_update.argtypes = C.c_int, [vp, vp, C.c_float]
+        lib.ref_gfx_pixels.restype, lib.ref_gfx_pixels.argtypes = C.c_int64, [vp, C.c_int64]
+        lib.ref_gfx_polylines.restype, lib.ref_gfx_polylines.argtypes = C.c_int64, [vp, C.c_int64, C.POINTER(C.c_int32)]
+        lib.ref_gfx_segments.restype, lib.ref_gfx_segments.argtypes = C.c_int64, [vp, C.c_int64]
+        self.lib, self.ref, self.visual = lib, ref, visual
+        self.h = vp()
+        assert lib.ref_gfx_create(C.byref(ref.cfg), C.byref(visual), C.byref(self.h)) == 0
+
+    def close(self):
+        if self.h:
+            self.lib.ref_gfx_destroy(self.h)
+            self.h = None
+
+    def update(self, d_t=None):
+        """-> (pixels (H, W) uint32, polylines (n_lines, length, 2) int32, segments (n, 4) int32)."""
+        assert self.lib.ref_gfx_update(self.h, self.ref.h, self.ref.cfg.d_t if d_t is None else d_t) == 0
+        n = self.lib.ref_gfx_pixels(None, 0)
+        pixels = np.zeros(n, np.uint32)
+        self.lib.ref_gfx_pixels(pixels.ctypes.data, n)
+        nl = C.c_int32()
+        n = self.lib.ref_gfx_polylines(None, 0, C.byref(nl))
+        pts = np.zeros(n, np.int32)
+        self.lib.ref_gfx_polylines(pts.ctypes.data, n, C.byref(nl))
+        n = self.lib.ref_gfx_segments(None, 0)
+        seg = np.zeros(n, np.int32)
+        self.lib.ref_gfx_segments(seg.ctypes.data, n)
+        H, W = self.ref.shape
+        return (pixels.reshape(H, W), pts.reshape(nl.value, -1, 2) if nl.value else pts.reshape(0, 0, 2),
+                seg.reshape(-1, 4))
+
+
+def ref_sample_velocity(ref: RefSim, xs, ys):
+    """Fluid::get_general_velocity evaluated by the reference's own device code."""
+    lib = ref.lib
+    vp = C.c_void_p
+    lib.ref_sample_velocity.restype, lib.ref_sample_velocity.argtypes = C.c_int, [vp, C.c_int, vp, vp, vp, vp]
+    xs = np.ascontiguousarray(xs, np.float32)
+    ys = np.ascontiguousarray(ys, np.float32)
+    ou, ov = np.empty_like(xs), np.empty_like(ys)
+    assert lib.ref_sample_velocity(ref.h, xs.size, xs.ctypes.data, ys.ctypes.data, ou.ctypes.data, ov.ctypes.data) == 0
+    return ou, ov

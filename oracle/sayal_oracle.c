@@ -24,6 +24,7 @@
  *
  * Layout: every array is W*H in the reference's order, index(i,j) = (H-1-j)*W + i (fluid.cu:163).
  */
+#define _GNU_SOURCE
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -416,10 +417,34 @@ void oracle_decay_smoke(oracle_sim* s, float d_t) {
   }
 }
 
-/* ---- Fluid::update (fluid.cu:770-795); diffusion excluded (H1: parity configs set viscosity 0) */
+/* ---- Fluid::apply_diffusion_at (fluid.cu:176-183), host loop (fluid.cu:185-190) ------------------
+ * The reference sweeps u in place, n launches, in whatever order the blocks run (H1: a data race).  The
+ * specification restated here fixes the order: cells with (i+j) even, then (i+j) odd — the same order the
+ * CUDA path uses; against the reference's racy binary the two differ by O(a^2) per sweep. */
+void oracle_diffusion(oracle_sim* s, int iterations, float d_t) {
+  const int W = s->W, H = s->H;
+  const float a = (s->c.viscosity * d_t) / (float)(s->h * s->h); /* fluid.cu:177, square(int) */
+  const float denom = fmaf(4.0f, a, 1.0f);                         /* 1 + 4 * a */
+  for (int it = 0; it < iterations; it++) {
+    for (int colour = 0; colour < 2; colour++) {
+#pragma omp parallel for num_threads(s->threads) schedule(static)
+      for (int j = 1; j < H - 1; j++) {
+        for (int i = 1 + ((j + 1 + colour) & 1); i < W - 1; i += 2) {
+          size_t k = IDX(s, i, j);
+          float sum = ((s->u[IDX(s, i - 1, j)] + s->u[IDX(s, i + 1, j)]) + s->u[IDX(s, i, j - 1)]) +
+                      s->u[IDX(s, i, j + 1)];
+          s->u[k] = fmaf(a, sum, s->u[k]) / denom;
+        }
+      }
+    }
+  }
+}
+
+/* ---- Fluid::update (fluid.cu:770-795) ------------------------------------------------------------ */
 void oracle_step(oracle_sim* s, const sayal_source* src, float d_t) {
   oracle_forces(s, src, d_t);
   if (s->c.enable_pressure) oracle_zero_pressure(s);
+  if (s->c.viscosity != 0) oracle_diffusion(s, s->c.proj_n, d_t); /* fluid.cu:775-777 */
   oracle_projection(s, s->c.proj_n, d_t);
   if (s->c.enable_pressure) oracle_pressure_range(s);
   oracle_extrapolation(s);
@@ -427,6 +452,80 @@ void oracle_step(oracle_sim* s, const sayal_source* src, float d_t) {
   if (s->c.enable_smoke && s->c.wt_smoke != 0) {
     oracle_advect_smoke(s, d_t);
     oracle_decay_smoke(s, d_t);
+  }
+}
+
+/* ---- Fluid::trace (fluid.cu:16-36) under GraphicsHandler::update_traces (graphics_handler.cu:358-421) ----
+ * static_cast<int>(round(x)): roundf (half away from zero), then the GPU's saturating conversion. */
+void oracle_path_lines(oracle_sim* s, const sayal_visual* vis, float d_t, int32_t* xs, int32_t* ys) {
+  const int dist = vis->path_line_distance, len = vis->path_line_length;
+  const int nx = s->W / dist, ny = s->H / dist;
+  for (int b = 0; b < ny; b++) {
+    for (int a = 0; a < nx; a++) {
+      const int i = a * dist, j = b * dist;
+      int32_t* lx = xs + ((size_t)(ny - 1 - b) * nx + a) * len;
+      int32_t* ly = ys + ((size_t)(ny - 1 - b) * nx + a) * len;
+      if (s->is_solid[IDX(s, i, j)]) {
+        for (int k = 0; k < len; k++) lx[k] = ly[k] = -1;
+        continue;
+      }
+      float px = pos_half(i, s->h), py = pos_half(j, s->h);
+      lx[0] = f2i(roundf(px));
+      ly[0] = s->H - 1 - f2i(roundf(py));
+      for (int k = 1; k < len; k++) {
+        float vx = general_velocity_x(s, px, py), vy = general_velocity_y(s, px, py);
+        px = fmaf(vx, d_t, px); /* position + velocity * d_t, contracted by nvcc */
+        py = fmaf(vy, d_t, py);
+        lx[k] = f2i(roundf(px));
+        ly[k] = s->H - 1 - f2i(roundf(py));
+      }
+    }
+  }
+}
+
+/* ---- update_center_velocity_arrow_at (graphics_handler.cu:317-335) + make_arrow_data (:168-200) ------
+ * The float transcendental calls of the source (atan2, cos, sin on float => atan2f, cosf, sinf) are evaluated in
+ * double and rounded to float: correctly rounded up to a 2^-29 chance, hence the same bits on the CPU and on the
+ * GPU.  (The reference's binary uses the fast-math approximations; its arrow tips may differ by one pixel.) */
+static inline float cosf_cr(float x) { return (float)cos((double)x); }
+static inline float sinf_cr(float x) { return (float)sin((double)x); }
+
+void oracle_arrows(oracle_sim* s, const sayal_visual* vis, sayal_arrow* out) {
+  const int dist = vis->arrows_distance, cs = vis->cell_pixel_size;
+  const int nx = s->W / dist, ny = s->H / dist;
+  const float head_angle = (float)(M_PI / 8); /* ARROW_HEAD_ANGLE, config.hpp:6 */
+  const float head_len = (float)vis->arrows_head_length;
+  for (int b = 0; b < ny; b++) {
+    for (int a = 0; a < nx; a++) {
+      const int i = a * dist, j = b * dist;
+      sayal_arrow* ar = out + (size_t)(ny - 1 - b) * nx + a;
+      memset(ar, 0, sizeof *ar);
+      if (s->is_solid[IDX(s, i, j)]) continue;
+      float x = (float)(((double)i + 0.5) * (double)cs);
+      float y = (float)(((double)(s->H - j - 1) + 0.5) * (double)cs);
+      float qy = (float)(s->H * cs) - y;
+      float vx = general_velocity_x(s, x, qy), vy = general_velocity_y(s, x, qy);
+      float angle = (float)atan2((double)vy, (double)vx);
+      float length = sqrtf(fmaf(vx, vx, vy * vy));
+      if (length < vis->arrows_disable_threshold) continue;
+      ar->valid = 1;
+      int sx = f2i(x), sy = f2i(y); /* make_arrow_data(int x, int y, ...) */
+      ar->start_x = sx;
+      ar->start_y = sy;
+      length *= vis->arrows_length_multiplier;
+      int x_off = f2i(length * cosf_cr(angle));
+      int y_off = f2i(-length * sinf_cr(angle));
+      ar->end_x = sx + x_off;
+      ar->end_y = sy + y_off;
+      int hx = f2i(-head_len * cosf_cr(angle + head_angle));
+      int hy = f2i(head_len * sinf_cr(angle + head_angle));
+      ar->left_head_end_x = ar->end_x + hx;
+      ar->left_head_end_y = ar->end_y + hy;
+      hx = f2i(-head_len * cosf_cr(head_angle - angle));
+      hy = f2i(-head_len * sinf_cr(head_angle - angle));
+      ar->right_head_end_x = ar->end_x + hx;
+      ar->right_head_end_y = ar->end_y + hy;
+    }
   }
 }
 

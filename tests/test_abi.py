@@ -4,7 +4,7 @@ import re
 from pathlib import Path
 
 from opensayal_b200 import LIB_PATH, load
-from opensayal_b200._abi import SYMBOLS, SayalConfig, SayalSlab, SayalSource
+from opensayal_b200._abi import SYMBOLS, SayalArrow, SayalConfig, SayalSlab, SayalSource, SayalVisual
 
 ROOT = Path(__file__).resolve().parent.parent
 
@@ -27,7 +27,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_load_and_version():
     lib = load()
-    assert lib.sayal_abi_version() == 1
+    assert lib.sayal_abi_version() == 2
     assert lib.sayal_last_error() is not None
 
 
@@ -36,6 +36,8 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(SayalConfig) == 31 * 4
     assert ctypes.sizeof(SayalSource) == 5 * 4
     assert ctypes.sizeof(SayalSlab) == 4 * 4
+    assert ctypes.sizeof(SayalVisual) == 17 * 4
+    assert ctypes.sizeof(SayalArrow) == 9 * 4
 
 
 def test_no_oracle_in_product():
