@@ -256,7 +256,8 @@ def bench_ours_single(args):
         "metric": "cell-steps/sec (n=50 SOR)", "value": value, "unit": "cell-steps/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_block(cfg, 1, {"temporal_block": sim.get_option("temporal_block") or 5,
+        "config": config_block(cfg, 1, {"temporal_block": sim.get_option("plan_temporal_block"),
+                                        "tile_rows_per_warp": sim.get_option("plan_rows_per_warp"),
                                         "projection_kernel": sim.get_option("projection_kernel")}),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
         "clocks": clocks.summary(),

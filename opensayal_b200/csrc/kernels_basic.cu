@@ -105,15 +105,6 @@ int launch_export_masks(Sim* s) {
 // ---------------------------------------------------------------------------------------------------
 // External forces: Fluid::apply_external_forces_at (fluid.cu:308-349), every cell (H14).
 // ---------------------------------------------------------------------------------------------------
-struct ForceArgs {
-  int band_lo, band_hi;    // H/2 - ph/2 .. H/2 + ph/2
-  int smoke_lo, smoke_hi;  // count == 1 band
-  int period, anchor;      // count != 1: (anchor - j) % period < smoke_height
-  float damping;           // expf(-drag*dt), evaluated once on the host (fluid.cu:332)
-  int src_active, src_x, src_y;
-  float src_smoke, src_velocity;
-  float d_t;
-};
 
 __global__ void forces_kernel(Grid g, Phys p, ForceArgs a, float* __restrict__ u, float* __restrict__ v,
                               float* __restrict__ smoke) {
@@ -149,7 +140,7 @@ __global__ void forces_kernel(Grid g, Phys p, ForceArgs a, float* __restrict__ u
   if (touch_u) u[k] = uu;
 }
 
-int launch_forces(Sim* s, const sayal_source* src, float d_t) {
+int launch_forces(Sim* s, const sayal_source* src, float d_t, bool may_fuse) {
   const Phys& p = s->ph;
   const int H = s->g.H;
   ForceArgs a;
@@ -168,6 +159,14 @@ int launch_forces(Sim* s, const sayal_source* src, float d_t) {
   a.src_smoke = src ? src->smoke : 0.f;
   a.src_velocity = src ? src->velocity : 0.f;
   a.d_t = d_t;
+  // No drag and no interactive source: what is left (v += g d_t, the inlet) is folded into the load of the
+  // step's first tiled projection pass (projection_pack.cu) when the caller runs one next.
+  if (may_fuse && s->fuse_forces && s->projection_kernel == 1 && !p.enable_pressure && s->cfg.proj_n > 0 &&
+      s->cfg.viscosity == 0.f && p.drag_coeff == 0.f && !a.src_active) {
+    s->fuse_args = a;
+    s->fuse_pending = 1;
+    return SAYAL_OK;
+  }
   dim3 block(128, 2);
   forces_kernel<<<cell_grid(s->g, s->g.local_rows, block), block, 0, s->stream>>>(s->g, p, a, s->u, s->v, s->smoke);
   SAYAL_LAUNCH_CHECK(s, "forces_kernel");

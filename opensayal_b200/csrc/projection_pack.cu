@@ -143,7 +143,60 @@ struct PackArgs {
   int stride_x;  // TW - 2*halo_x
   int stride_y;  // TH - 2*halo_y
   long long* timeline;  // profiling only (option "debug_timeline"): 5 x int64 per CTA, or null
+  // External forces folded into the load of a step's first pass (apply_external_forces_at, fluid.cu:308-349, in
+  // the form it takes with no drag and no interactive source: v += g d_t everywhere, u = speed and smoke = value
+  // on the inlet cells).  Tiles overlap, so a cell's forces are evaluated by every tile that loads it — the
+  // same operation on the same input, hence the same bits — and the pass writes every cell exactly once.
+  int extrap_on;  // the step's last pass: apply_extrapolation_at (fluid.cu:720-733) on the tile before it is stored
+  int force_on;
+  float force_g, force_dt, wt_speed, wt_smoke;
+  int inlet_len, band_lo, band_hi, smoke_lo, smoke_hi, smoke_count, smoke_height, period, anchor;
+  float* smoke;
 };
+
+// forces for the four cells (x..x+3, memory row lr) a lane has just loaded.  Registers only: a store here would
+// sit between the tile's loads and serialise them (the inlet smoke is written by forces_inlet_smoke afterwards).
+__device__ __forceinline__ bool inlet_band(const PackArgs& a, int lr, bool* smoke_on) {
+  const Grid& g = a.g;
+  const int j = g.H - 1 - (g.row_base + lr);
+  *smoke_on = a.smoke_count == 1 ? (j >= a.smoke_lo && j <= a.smoke_hi)
+                                 : (a.period != 0 && (a.anchor - j) % a.period < a.smoke_height);
+  return j >= a.band_lo && j <= a.band_hi;
+}
+
+__device__ __forceinline__ void forces_on_load(const PackArgs& a, int x, int lr, float4& uu, float4& vv) {
+  const Grid& g = a.g;
+  if (x + 3 < g.W) {
+    vv.x = __fmaf_rn(a.force_g, a.force_dt, vv.x);
+    vv.y = __fmaf_rn(a.force_g, a.force_dt, vv.y);
+    vv.z = __fmaf_rn(a.force_g, a.force_dt, vv.z);
+    vv.w = __fmaf_rn(a.force_g, a.force_dt, vv.w);
+  } else {  // the lane that straddles W: pad columns are not cells
+    if (x < g.W) vv.x = __fmaf_rn(a.force_g, a.force_dt, vv.x);
+    if (x + 1 < g.W) vv.y = __fmaf_rn(a.force_g, a.force_dt, vv.y);
+    if (x + 2 < g.W) vv.z = __fmaf_rn(a.force_g, a.force_dt, vv.z);
+  }
+  if (x <= a.inlet_len) {  // wind-tunnel inlet (fluid.cu:318-330): columns 1..smoke_length of the pipe band
+    bool on;
+    if (inlet_band(a, lr, &on)) {
+      if (x + 0 != 0 && x + 0 <= a.inlet_len && x + 0 < g.W) uu.x = a.wt_speed;
+      if (x + 1 <= a.inlet_len && x + 1 < g.W) uu.y = a.wt_speed;
+      if (x + 2 <= a.inlet_len && x + 2 < g.W) uu.z = a.wt_speed;
+      if (x + 3 <= a.inlet_len && x + 3 < g.W) uu.w = a.wt_speed;
+    }
+  }
+}
+
+// smoke = wind_tunnel.smoke on the inlet cells of the smoke bands (fluid.cu:321-329) for one lane's row
+__device__ __forceinline__ void forces_inlet_smoke(const PackArgs& a, int x, int lr) {
+  const Grid& g = a.g;
+  bool on;
+  if (x > a.inlet_len || !inlet_band(a, lr, &on) || !on) return;
+  float* sm = a.smoke + (size_t)lr * g.pitch + x;
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+    if (x + c != 0 && x + c <= a.inlet_len && x + c < g.W) sm[c] = a.wt_smoke;
+}
 
 __device__ __forceinline__ long long globaltimer() {
   long long t;
@@ -222,7 +275,10 @@ __device__ __forceinline__ void half_sweep(u64 (&U02)[RY], u64 (&U13)[RY], u64 (
   }
 }
 
-template <int RY, int NW>
+// FORCES: the step's first pass, which also applies the external forces while loading (a separate instantiation,
+// so the other passes keep their register allocation).
+// EXTRAP: the step's last pass, which also applies the boundary extrapolation before storing.
+template <int RY, int NW, bool FORCES, bool EXTRAP>
 __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a) {
   constexpr int TH = RY * NW;
   // shared v rows: sv[0] is the v row above the tile (read-only halo), sv[w+1] is the last row of warp w.
@@ -265,6 +321,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
       uu = *reinterpret_cast<const float4*>(a.u_in + k);
       vv = *reinterpret_cast<const float4*>(a.v_in + k);
       f = *reinterpret_cast<const unsigned*>(a.flags + k);
+      if (FORCES) forces_on_load(a, x, lr, uu, vv);
     }
     U02[r] = pk(uu.x, uu.z);
     U13[r] = pk(uu.y, uu.w);
@@ -276,6 +333,11 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
       vlast13 = pk(vv.y, vv.w);
     }
     fl[r] = f;
+  }
+  if (FORCES && x <= a.inlet_len) {  // tiles overlap: every tile that holds an inlet cell stores the same value
+#pragma unroll
+    for (int r = 0; r < RY; r++)
+      if (lr0 + r < g.local_rows) forces_inlet_smoke(a, x, lr0 + r);
   }
   // The tile's last column has no column to its right: that cell only lends its faces (carrier).
   if (lane == 31) {
@@ -293,7 +355,13 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   sts64(sv_bot + 64, vlast13);
   if (w == 0) {
     float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (col_ok && Y0 >= 1 && Y0 - 1 < g.local_rows) vv = *reinterpret_cast<const float4*>(a.v_in + (size_t)(Y0 - 1) * g.pitch + x);
+    if (col_ok && Y0 >= 1 && Y0 - 1 < g.local_rows) {
+      vv = *reinterpret_cast<const float4*>(a.v_in + (size_t)(Y0 - 1) * g.pitch + x);
+      if (FORCES) {
+        float4 unused = make_float4(0.f, 0.f, 0.f, 0.f);
+        forces_on_load(a, x, Y0 - 1, unused, vv);
+      }
+    }
     sts64(sv_top, pk(vv.x, vv.z));
     sts64(sv_top + 64, pk(vv.y, vv.w));
   }
@@ -372,6 +440,62 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   vlast13 = lds64(sv_bot + 64);
   if (tl && threadIdx.x == 0) tl[2] = globaltimer();
 
+  // Boundary extrapolation folded into the step's last pass: the closed form of the canonical order (all
+  // j-rules, then all i-rules; see extrapolation_kernel in kernels_basic.cu) applied to the registers.  Every
+  // source value sits in the same tile as its destination: rows j = 0, 1 (and H-1, H-2) are the last (first) two
+  // rows of the domain, inside the un-haloed edge of the tiles that hold them; columns 0, 1 share a lane.
+  if (EXTRAP) {
+    const int lrA = g.H - 2 - g.row_base, lrB = lrA + 1;  // memory rows of j = 1 and j = 0
+    // u(i, H-1) = u(i, H-2): memory rows 0 and 1, both rows of warp 0 of the top tiles
+    if (g.row_base == 0 && Y0 == 0 && w == 0 && g.local_rows >= 2) {
+      U02[0] = U02[1];
+      U13[0] = U13[1];
+    }
+    // u(i, 0) = u(i, 1): the two rows may sit in different warps, so row j = 1 travels through shared memory
+    if (lrA >= Y0 && lrA >= 0 && lrB < g.local_rows && lrB < Y0 + TH) {  // uniform over the CTA
+      float4* scratch = reinterpret_cast<float4*>(&sv[0][0]);
+#pragma unroll
+      for (int r = 0; r < RY; r++)
+        if (lr0 + r == lrA) scratch[lane] = make_float4(lo(U02[r]), lo(U13[r]), hi(U02[r]), hi(U13[r]));
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < RY; r++)
+        if (lr0 + r == lrB) {
+          float4 t = scratch[lane];
+          U02[r] = pk(t.x, t.z);
+          U13[r] = pk(t.y, t.w);
+        }
+    }
+    const int xl = (g.W - 1) & ~3, cl = (g.W - 1) & 3;  // lane and component of column W-1
+#pragma unroll
+    for (int r = 0; r < RY; r++) {
+      u64 p02 = r < RY - 1 ? V02[r < RY - 1 ? r : 0] : vlast02;
+      u64 p13 = r < RY - 1 ? V13[r < RY - 1 ? r : 0] : vlast13;
+      if (lr0 + r == lrA) {  // v(i, 1) = 0
+        p02 = 0ull;
+        p13 = 0ull;
+      } else {
+        if (x == 0) p02 = pk(lo(p13), hi(p02));  // v(0, j) = v(1, j)
+        if (cl == 0) {                           // v(W-1, j) = v(W-2, j): column W-2 is the previous lane's last
+          float prev = __shfl_up_sync(FULL, hi(p13), 1);
+          if (x == xl) p02 = pk(prev, hi(p02));
+        } else if (x == xl) {
+          if (cl == 1) p13 = pk(lo(p02), hi(p13));
+          else if (cl == 2) p02 = pk(lo(p02), lo(p13));
+          else p13 = pk(lo(p13), hi(p02));
+        }
+      }
+      if (x == 0) U13[r] = pk(0.f, hi(U13[r]));  // u(1, j) = 0
+      if (r < RY - 1) {
+        V02[r < RY - 1 ? r : 0] = p02;
+        V13[r < RY - 1 ? r : 0] = p13;
+      } else {
+        vlast02 = p02;
+        vlast13 = p13;
+      }
+    }
+  }
+
   // write the part of the tile that is exact: everything >= halo away from an edge that has a neighbour
   const int vx0 = X0 == 0 ? 0 : X0 + a.halo_x;
   const int vx1 = X0 + TW >= g.pitch ? g.pitch : X0 + TW - a.halo_x;
@@ -398,13 +522,12 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
 
 struct Variant {
   int ry, nw;
-  void (*kernel)(PackArgs);
+  void (*kernel[4])(PackArgs);  // indexed by (forces on load) | (extrapolation before store) << 1
 };
-const Variant kVariants[] = {
-    {8, 16, projection_pack_kernel<8, 16>},
-    {10, 16, projection_pack_kernel<10, 16>},
-    {12, 16, projection_pack_kernel<12, 16>},
-};
+#define SAYAL_PACK_VARIANT(RY, NW)                                                                          \
+  {RY, NW, {projection_pack_kernel<RY, NW, false, false>, projection_pack_kernel<RY, NW, true, false>,     \
+            projection_pack_kernel<RY, NW, false, true>, projection_pack_kernel<RY, NW, true, true>}}
+const Variant kVariants[] = {SAYAL_PACK_VARIANT(8, 16), SAYAL_PACK_VARIANT(10, 16), SAYAL_PACK_VARIANT(12, 16)};
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kMaxT = 16;
 
@@ -450,7 +573,7 @@ int launch_pass(Sim* s, const Variant& v, const PackArgs& a, dim3 grid, cudaStre
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr;
   lc.numAttrs = s->use_pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&lc, v.kernel, a);
+  cudaError_t e = cudaLaunchKernelEx(&lc, v.kernel[(a.force_on ? 1 : 0) | (a.extrap_on ? 2 : 0)], a);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
     char m[256];
@@ -461,11 +584,15 @@ int launch_pass(Sim* s, const Variant& v, const PackArgs& a, dim3 grid, cudaStre
   return SAYAL_OK;
 }
 
-int run_passes(Sim* s, int variant, int T, int iterations) {
+int run_passes(Sim* s, int variant, int T, int iterations, bool with_forces = false, bool with_extrap = false) {
   const Variant& v = kVariants[variant];
+  // ceil(iterations / T) passes of nearly equal size (25 at T = 10 -> 9, 8, 8 rather than 10, 10, 5): the same
+  // number of loads and stores, but narrower halos on every pass
+  const int passes = (iterations + T - 1) / T;
+  const int base = iterations / passes, longer = iterations % passes;
   int done = 0;
-  while (done < iterations) {
-    int it = iterations - done < T ? iterations - done : T;
+  for (int pass = 0; pass < passes; pass++) {
+    int it = base + (pass < longer ? 1 : 0);
     Geometry q;
     if (!geometry(s->g, v, it, &q)) return set_error(SAYAL_EINVAL, "projection tile: temporal block too large for the tile");
     PackArgs a;
@@ -481,6 +608,17 @@ int run_passes(Sim* s, int variant, int T, int iterations) {
     a.halo_y = q.halo_y;
     a.stride_x = q.stride_x;
     a.stride_y = q.stride_y;
+    a.extrap_on = with_extrap && pass == passes - 1;
+    a.force_on = with_forces && done == 0;
+    a.smoke = s->smoke;
+    if (a.force_on) {
+      const ForceArgs& f = s->fuse_args;
+      const Phys& ph = s->ph;
+      a.force_g = ph.g; a.force_dt = f.d_t; a.wt_speed = ph.wt_speed; a.wt_smoke = ph.wt_smoke;
+      a.inlet_len = ph.wt_smoke_length; a.band_lo = f.band_lo; a.band_hi = f.band_hi;
+      a.smoke_lo = f.smoke_lo; a.smoke_hi = f.smoke_hi; a.smoke_count = ph.wt_smoke_count;
+      a.smoke_height = ph.wt_smoke_height; a.period = f.period; a.anchor = f.anchor;
+    }
     a.timeline = s->d_timeline;  // the last pass wins: profile single passes
     if (s->d_timeline && (size_t)q.tiles_x * q.tiles_y * 5 > s->timeline_cap) a.timeline = nullptr;
     s->timeline_tiles = a.timeline ? q.tiles_x * q.tiles_y : 0;
@@ -497,6 +635,19 @@ int run_passes(Sim* s, int variant, int T, int iterations) {
 }  // namespace
 
 int tiled_max_temporal_block() { return kMaxT; }
+
+// CUDA loads a kernel lazily at its first launch, and loading may wait for the device to drain.  A linked slab
+// must never meet that wait in the middle of a step (its neighbour may be spinning for it), so every variant is
+// loaded when the sim is created.
+int tiled_preload() {
+  for (int v = 0; v < kNumVariants; v++)
+    for (int m = 0; m < 4; m++) {
+      cudaFuncAttributes fa;
+      cudaError_t e = cudaFuncGetAttributes(&fa, kVariants[v].kernel[m]);
+      if (e != cudaSuccess) return set_error(SAYAL_ECUDA, cudaGetErrorString(e));
+    }
+  return SAYAL_OK;
+}
 
 // Choose (tile variant, temporal block) for `iterations` SOR iterations on this grid: rank all candidates
 // with the wave-quantisation model, then time the best few on the live arrays (state saved and restored;
@@ -518,6 +669,10 @@ int tiled_prepare(Sim* s, int iterations) {
     for (int T = 1; T <= kMaxT && T <= iterations; T++) {
       if (s->temporal_block > 0 && T != (s->temporal_block < iterations ? s->temporal_block : iterations)) continue;
       if (s->force_variant >= 0 && v != s->force_variant) continue;
+      {  // run_passes splits evenly: T and ceil(n / passes(T)) describe the same plan, keep the canonical one
+        int passes = (iterations + T - 1) / T;
+        if (s->temporal_block <= 0 && (iterations + passes - 1) / passes != T) continue;
+      }
       double c = model_cost(s->g, kVariants[v], T, iterations, sms);
       if (c < 1e29) cands[nc++] = {v, T, c, 0.f};
     }
@@ -528,7 +683,8 @@ int tiled_prepare(Sim* s, int iterations) {
   int best = 0;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(s->stream, &cap);
-  int ntime = nc < 8 ? nc : 8;
+  // time the model's best 8 candidates always, the rest while the tuning budget (about 0.25 s) lasts
+  int ntime = nc;
   if (s->autotune && cap == cudaStreamCaptureStatusNone && ntime > 1) {
     size_t bytes = sizeof(float) * (size_t)s->g.pitch * s->g.local_rows;
     float *su = nullptr, *sv = nullptr;
@@ -542,7 +698,9 @@ int tiled_prepare(Sim* s, int iterations) {
       int parity = s->parity;
       float *u0 = s->u, *v0 = s->v, *ub0 = s->u_buf, *vb0 = s->v_buf;
       float best_ms = 1e30f;
+      float spent_ms = 0.f;
       for (int c = 0; c < ntime; c++) {
+        if (c >= 8 && spent_ms > 250.f) break;
         float ms_min = 1e30f;
         for (int rep = 0; rep < 3; rep++) {  // first repetition warms the instruction cache
           cudaEventRecord(e0, s->stream);
@@ -551,6 +709,7 @@ int tiled_prepare(Sim* s, int iterations) {
           if (r != SAYAL_OK || cudaEventSynchronize(e1) != cudaSuccess) { ms_min = 1e30f; break; }
           float ms = 0.f;
           cudaEventElapsedTime(&ms, e0, e1);
+          spent_ms += ms;
           if (rep > 0 && ms < ms_min) ms_min = ms;
         }
         cands[c].ms = ms_min;
@@ -581,7 +740,10 @@ int launch_projection_tiled(Sim* s, int iterations, float d_t) {
   if (s->ph.enable_pressure) return launch_projection_plain(s, iterations, d_t);  // pressure accumulates per cell: plain path
   int r = tiled_prepare(s, iterations);
   if (r != SAYAL_OK) return r;
-  return run_passes(s, s->plan_variant, s->plan_T, iterations);
+  const bool with_forces = s->fuse_pending != 0, with_extrap = s->fuse_extrap != 0;
+  s->fuse_pending = 0;
+  s->fuse_extrap = with_extrap ? 2 : 0;  // 2 = done: the caller skips the extrapolation kernel
+  return run_passes(s, s->plan_variant, s->plan_T, iterations, with_forces, with_extrap);
 }
 
 }  // namespace sayal

@@ -146,6 +146,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   s->temporal_block = 0;  // 0 = auto
   s->use_graph = 1;
   s->use_pdl = 1;
+  s->fuse_forces = 1;
   s->advect_kernel = 2;
   s->overlap_exchange = 1;
   s->advect_margin = 16;
@@ -163,6 +164,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   if (const char* e = getenv("SAYAL_ADVECT_MARGIN")) { int m = atoi(e); if (m >= 2) s->advect_margin = m; }
   if (const char* e = getenv("SAYAL_OVERLAP_EXCHANGE")) s->overlap_exchange = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_USE_PDL")) s->use_pdl = atoi(e) != 0;
+  if (const char* e = getenv("SAYAL_FUSE_FORCES")) s->fuse_forces = atoi(e) != 0;
 
   auto fail = [&](int code) {
     free_sim(s);
@@ -198,6 +200,8 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   e = cudaMalloc(&s->geo, field_elems(s) * sizeof(uint16_t));
   if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
   r = launch_build_geo(s);
+  if (r != SAYAL_OK) return fail(r);
+  r = tiled_preload();
   if (r != SAYAL_OK) return fail(r);
   e = cudaStreamSynchronize(s->stream);
   if (e != cudaSuccess) return fail(set_error(SAYAL_ECUDA, cudaGetErrorString(e)));
@@ -294,7 +298,8 @@ bool is_linked(const Sim* s);
 
 static int step_impl(Sim* s, const sayal_source* src, float d_t) {
   const bool linked = is_linked(s);
-  TRY(launch_forces(s, src, d_t));
+  const int skip = s->debug_skip;  // profiling only: marginal cost of a stage inside the replayed graph
+  if (!(skip & 1)) TRY(launch_forces(s, src, d_t, true));  // may defer to the first projection pass (fuse_forces)
   if (s->ph.enable_pressure) TRY(launch_zero_pressure(s));
   // apply_diffusion (fluid.cu:775-777): n sweeps over u when viscosity != 0, in a fixed red-black order (H1).
   // A sweep has the same one-row dependency radius per colour as a projection half-sweep, so linked slabs chunk it
@@ -315,8 +320,12 @@ static int step_impl(Sim* s, const sayal_source* src, float d_t) {
   // of depth, an exchange restores D = halo.  Exchanges happen only when the next operation needs more depth
   // than is left, and once at the end of the step (u, v and smoke together).
   int D = s->slab_halo;
+  // the pass that ends the projection also applies the boundary extrapolation (fuse_forces covers both folds)
+  const bool fold_extrap = s->fuse_forces && s->projection_kernel == 1 && !s->ph.enable_pressure && s->cfg.proj_n > 0;
+  s->fuse_extrap = 0;
   if (!linked) {
-    TRY(projection(s, s->cfg.proj_n, d_t));
+    s->fuse_extrap = fold_extrap && !(skip & 2);
+    if (!(skip & 16)) TRY(projection(s, s->cfg.proj_n, d_t));
   } else {
     for (int done = 0; done < s->cfg.proj_n;) {
       if (D < 2) {
@@ -324,6 +333,7 @@ static int step_impl(Sim* s, const sayal_source* src, float d_t) {
         D = s->slab_halo;
       }
       int k = s->cfg.proj_n - done < D / 2 ? s->cfg.proj_n - done : D / 2;
+      s->fuse_extrap = fold_extrap && done + k == s->cfg.proj_n;
       TRY(projection(s, k, d_t));
       D -= 2 * k;
       done += k;
@@ -333,10 +343,11 @@ static int step_impl(Sim* s, const sayal_source* src, float d_t) {
     TRY(launch_pressure_range(s));
     s->range_valid = false;
   }
-  TRY(launch_extrapolation(s));
+  if (s->fuse_extrap != 2 && !(skip & 2)) TRY(launch_extrapolation(s));
+  s->fuse_extrap = 0;
   if (!linked) {
-    TRY(advect_velocity(s, d_t));
-    if (s->ph.enable_smoke && s->ph.wt_smoke != 0.f) TRY(advect_smoke(s, d_t));  // decay fused (fluid.cu:792)
+    if (!(skip & 4)) TRY(advect_velocity(s, d_t));
+    if (s->ph.enable_smoke && s->ph.wt_smoke != 0.f && !(skip & 8)) TRY(advect_smoke(s, d_t));  // decay fused (fluid.cu:792)
   } else {
     const bool smoke = s->ph.enable_smoke && s->ph.wt_smoke != 0.f;
     // velocity is advected on the owned rows and one ghost row each side; its gathers reach advect_margin rows
@@ -775,6 +786,10 @@ int sayal_set_option(sayal_sim* sim, const char* key, int64_t value) {
     s->overlap_exchange = value != 0;
   } else if (!strcmp(key, "use_pdl")) {
     s->use_pdl = value != 0;
+  } else if (!strcmp(key, "fuse_forces")) {
+    s->fuse_forces = value != 0;
+  } else if (!strcmp(key, "debug_skip")) {
+    s->debug_skip = (int)value;
   } else if (!strcmp(key, "debug_timeline")) {  // profiling only: per-CTA phase timestamps (sayal_debug_timeline)
     if (value && !s->d_timeline) {
       s->timeline_cap = 5 * 65536;
@@ -796,6 +811,7 @@ int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value) {
   else if (!strcmp(key, "temporal_block")) *value = s->temporal_block;
   else if (!strcmp(key, "use_graph")) *value = s->use_graph;
   else if (!strcmp(key, "use_pdl")) *value = s->use_pdl;
+  else if (!strcmp(key, "fuse_forces")) *value = s->fuse_forces;
   else if (!strcmp(key, "advect_kernel")) *value = s->advect_kernel;
   else if (!strcmp(key, "autotune")) *value = s->autotune;
   else if (!strcmp(key, "plan_temporal_block")) *value = s->plan_variant >= 0 ? s->plan_T : 0;

@@ -54,6 +54,17 @@ struct Phys {
   float obstacle_radius;
 };
 
+// Host-evaluated parameters of apply_external_forces_at (fluid.cu:308-349) for one step.
+struct ForceArgs {
+  int band_lo, band_hi;    // H/2 - ph/2 .. H/2 + ph/2
+  int smoke_lo, smoke_hi;  // count == 1 band
+  int period, anchor;      // count != 1: (anchor - j) % period < smoke_height
+  float damping;           // expf(-drag*dt), evaluated once on the host (fluid.cu:332)
+  int src_active, src_x, src_y;
+  float src_smoke, src_velocity;
+  float d_t;
+};
+
 // Device-side view of a slab's links to its two neighbours (slab_exchange.cu); side 0 = low memory rows.
 struct SlabLinkDev {
   float* peer_recv[2];    // where my edge rows land in the neighbour's block (null: no neighbour on that side)
@@ -89,7 +100,11 @@ struct Sim {
   int use_graph;
   int advect_kernel;      // 0 plain per-cell kernels, 1 shared-memory tiles, 2 direct with geometry words (cell_size 1)
   int use_pdl;            // programmatic dependent launch between projection passes
-  int fuse_forces;
+  int fuse_forces;        // option: fold the forces into the load of the step's first projection pass (default 1)
+  int fuse_pending;       // the step's forces have not been applied yet: the next tiled pass applies them
+  ForceArgs fuse_args;
+  int debug_skip;         // profiling only (option "debug_skip"): bit mask of step stages to leave out (wrong results!)
+  int fuse_extrap;        // 1: the next tiled projection call ends the step's projection and also extrapolates; 2: it did
   int autotune;           // time candidate tile plans on first use
   int force_variant;      // -1 = any tile variant
   int plan_variant, plan_T;  // tile plan of the last projection (projection_pack.cu)
@@ -130,7 +145,7 @@ struct Sim {
 // ---- kernels_basic.cu ---------------------------------------------------------------------------
 int launch_build_flags(Sim* s);
 int launch_export_masks(Sim* s);
-int launch_forces(Sim* s, const sayal_source* src, float d_t);
+int launch_forces(Sim* s, const sayal_source* src, float d_t, bool may_fuse = false);
 int launch_zero_pressure(Sim* s);
 int launch_projection_plain(Sim* s, int iterations, float d_t);
 int launch_pressure_range(Sim* s);
@@ -161,6 +176,7 @@ int launch_arrows(Sim* s, const sayal_visual* v, int nx, int ny, sayal_arrow* d_
 // ---- projection_pack.cu --------------------------------------------------------------------------
 int launch_projection_tiled(Sim* s, int iterations, float d_t);
 int tiled_max_temporal_block();
+int tiled_preload();  // load every kernel variant now (never lazily in the middle of a linked step)
 int tiled_prepare(Sim* s, int iterations);  // choose the tile plan (may time candidates; not capturable)
 
 

@@ -186,6 +186,36 @@ def test_full_steps_bit_exact(name):
         assert (gpu.min_pressure, gpu.max_pressure) == cpu.pressure_range()
 
 
+@pytest.mark.parametrize("width,height", [(203, 157), (384, 216), (517, 301)])
+def test_forces_folded_into_first_projection_pass(width, height):
+    """fuse_forces (default): v += g d_t and the inlet are applied while the step's first tiled pass loads its
+    tile, and the boundary extrapolation while the last pass stores.  Same bits as the separate kernels and as the
+    oracle — with gravity, an inlet wider than one lane's four columns, several smoke bands, and widths with
+    W % 4 = 3, 0, 1 (column W-2 in the same lane as W-1, or in the previous one)."""
+    cfg = Config.defaults(width, height, **{"fluid.viscosity": 0.0, "sim.physics.g": -4.0, "sim.projection.n": 13,
+                                            "sim.wind_tunnel.speed": 80.0, "sim.wind_tunnel.smoke_length": 6,
+                                            "sim.wind_tunnel.smoke_count": 3, "sim.wind_tunnel.smoke_height": 5,
+                                            "sim.wind_tunnel.pipe_height": height // 3})
+    fused, cpu = pair(cfg)
+    plain, _ = pair(cfg)
+    plain.set_option("fuse_forces", 0)
+    assert fused.get_option("fuse_forces") == 1
+    for step in range(3):
+        l0, l1 = fused.launch_count, plain.launch_count
+        fused.update(None, cfg.c.d_t)
+        plain.update(None, cfg.c.d_t)
+        cpu.step(None, cfg.c.d_t)
+        assert_same(fused, cpu, what=f"fused, step {step}")
+        assert_same(plain, cpu, what=f"separate kernel, step {step}")
+        assert (plain.launch_count - l1) - (fused.launch_count - l0) == 2  # forces and extrapolation kernels are gone
+    fused.run(2)
+    plain.run(2)
+    for _ in range(2):
+        cpu.step(None, cfg.c.d_t)
+    assert_same(fused, cpu, what="fused, graph replay")
+    assert_same(plain, cpu, what="separate kernel, graph replay")
+
+
 def test_interactive_source_steps():
     cfg = baseline_config(0)
     cfg["sim.projection.n"] = 10
