@@ -43,6 +43,8 @@ static void free_sim(Sim* s) {
   float* f[] = {s->u, s->v, s->p, s->smoke, s->u_buf, s->v_buf, s->smoke_buf};
   for (float* q : f)
     if (q) cudaFree(q);
+  for (int k = 0; k < s->n_orders; k++)
+    if (s->orders[k].order) cudaFree(s->orders[k].order);
   if (s->flags) cudaFree(s->flags);
   if (s->geo) cudaFree(s->geo);
   if (s->d_is_solid) cudaFree(s->d_is_solid);
@@ -147,6 +149,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   s->use_graph = 1;
   s->use_pdl = 1;
   s->fuse_forces = 1;
+  s->order_tiles = 1;
   s->advect_kernel = 2;
   s->overlap_exchange = 1;
   s->advect_margin = 16;
@@ -165,6 +168,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   if (const char* e = getenv("SAYAL_OVERLAP_EXCHANGE")) s->overlap_exchange = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_USE_PDL")) s->use_pdl = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_FUSE_FORCES")) s->fuse_forces = atoi(e) != 0;
+  if (const char* e = getenv("SAYAL_ORDER_TILES")) s->order_tiles = atoi(e) != 0;
 
   auto fail = [&](int code) {
     free_sim(s);
@@ -788,6 +792,9 @@ int sayal_set_option(sayal_sim* sim, const char* key, int64_t value) {
     s->use_pdl = value != 0;
   } else if (!strcmp(key, "fuse_forces")) {
     s->fuse_forces = value != 0;
+  } else if (!strcmp(key, "order_tiles")) {
+    s->order_tiles = value != 0;
+    s->plan_variant = -1, s->n_plans = 0;
   } else if (!strcmp(key, "debug_skip")) {
     s->debug_skip = (int)value;
   } else if (!strcmp(key, "debug_timeline")) {  // profiling only: per-CTA phase timestamps (sayal_debug_timeline)
@@ -812,6 +819,7 @@ int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value) {
   else if (!strcmp(key, "use_graph")) *value = s->use_graph;
   else if (!strcmp(key, "use_pdl")) *value = s->use_pdl;
   else if (!strcmp(key, "fuse_forces")) *value = s->fuse_forces;
+  else if (!strcmp(key, "order_tiles")) *value = s->order_tiles;
   else if (!strcmp(key, "advect_kernel")) *value = s->advect_kernel;
   else if (!strcmp(key, "autotune")) *value = s->autotune;
   else if (!strcmp(key, "plan_temporal_block")) *value = s->plan_variant >= 0 ? s->plan_T : 0;

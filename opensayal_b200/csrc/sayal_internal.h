@@ -111,6 +111,11 @@ struct Sim {
   static constexpr int kMaxPlans = 8;
   struct Plan { int iterations, variant, T; } plans[kMaxPlans];  // one per iteration count seen
   int n_plans;
+  // issue order of the tiles (most expensive first) per tile geometry, built on first use (projection_pack.cu)
+  int order_tiles;        // option (default 1)
+  static constexpr int kMaxOrders = 64;
+  struct TileOrder { int variant, it; int* order; } orders[kMaxOrders];
+  int n_orders;
   // CUDA graph cache for sayal_run: one single-step graph per starting buffer parity, with the
   // pointer assignment the step leaves behind (the step swaps front and back buffers)
   cudaGraphExec_t graph[4];   // indexed by `parity`

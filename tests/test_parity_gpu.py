@@ -259,6 +259,23 @@ def test_tile_ending_exactly_on_the_last_column(width, T):
     assert_same(gpu, cpu, names=("u", "v"), what=f"exact fit W={width} T={T}")
 
 
+@pytest.mark.parametrize("graph", [0, 1])
+def test_tile_issue_order_changes_no_bit(graph):
+    """order_tiles (default): tiles with walls / obstacle rims are issued first.  Any order gives the same bits."""
+    cfg = baseline_config(1, width=1000, height=700)
+    cfg["sim.projection.n"] = 9
+    a, cpu = pair(cfg)
+    b, _ = pair(cfg)
+    b.set_option("order_tiles", 0)
+    for f in (a, b):
+        f.set_option("use_graph", graph)
+        f.run(3)
+    for _ in range(3):
+        cpu.step(None, cfg.c.d_t)
+    assert_same(a, cpu, what="ordered tiles")
+    assert_same(b, cpu, what="row-major tiles")
+
+
 def test_autotuned_plan_is_invisible():
     """The autotuner times candidate plans on the live arrays; state, results and launch count must not show it."""
     cfg = baseline_config(1, width=640, height=400)
