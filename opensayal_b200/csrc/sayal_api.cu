@@ -177,7 +177,9 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) return fail(set_error(SAYAL_ECUDA, cudaGetErrorString(e)));
   if (s->slab_halo > 0) {  // slabs: a second stream for exchanges that overlap interior compute
-    e = cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // exchanges overtake the compute they run under
+    e = cudaStreamCreateWithPriority(&s->aux_stream, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming);
     if (e != cudaSuccess) return fail(set_error(SAYAL_ECUDA, cudaGetErrorString(e)));
@@ -271,29 +273,37 @@ static int advect_linked(Sim* s, float d_t, bool smoke, int ghost, int exchange_
   const int lo = g.own_lo - ghost < 0 ? 0 : g.own_lo - ghost;
   const int hi = g.own_hi + ghost > g.local_rows ? g.local_rows : g.own_hi + ghost;
   const bool overlap = exchange_mask && s->overlap_exchange && s->aux_stream && g.own_hi - g.own_lo >= 4 * halo;
+  auto swap_fields = [&]() {
+    if (smoke) {
+      swap_ptr(s->smoke, s->smoke_buf);
+      s->parity ^= 2;
+    } else {
+      swap_ptr(s->u, s->u_buf);
+      swap_ptr(s->v, s->v_buf);
+      s->parity ^= 1;
+    }
+  };
   if (overlap) {
     TRY(advect_rows(s, d_t, smoke, lo, g.own_lo + halo));
     TRY(advect_rows(s, d_t, smoke, g.own_hi - halo, hi));
     CUDA_TRY(cudaEventRecord(s->ev_fork, s->stream));
     CUDA_TRY(cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0));
+    // The exchange is enqueued BEFORE the interior rows: its few fat CTAs must find room while the SMs are empty
+    // (behind a grid of thousands of small blocks they would only be placed when that grid drains, i.e. the
+    // exchange would run after the advection instead of under it).  It reads the edge rows the two kernels above
+    // wrote into the back buffers and writes their ghost rows; the interior kernel touches neither.
+    swap_fields();  // the exchange sees the new arrays ...
+    int r = launch_slab_exchange_on(s, exchange_mask, s->aux_stream);
+    swap_fields();  // ... the interior kernel the old ones
+    if (r != SAYAL_OK) return r;
+    CUDA_TRY(cudaEventRecord(s->ev_join, s->aux_stream));
     TRY(advect_rows(s, d_t, smoke, g.own_lo + halo, g.own_hi - halo));
+    swap_fields();
+    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
   } else {
     TRY(advect_rows(s, d_t, smoke, lo, hi));
-  }
-  if (smoke) {
-    swap_ptr(s->smoke, s->smoke_buf);
-    s->parity ^= 2;
-  } else {
-    swap_ptr(s->u, s->u_buf);
-    swap_ptr(s->v, s->v_buf);
-    s->parity ^= 1;
-  }
-  if (overlap) {
-    TRY(launch_slab_exchange_on(s, exchange_mask, s->aux_stream));
-    CUDA_TRY(cudaEventRecord(s->ev_join, s->aux_stream));
-    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
-  } else if (exchange_mask) {
-    TRY(launch_slab_exchange(s, exchange_mask));
+    swap_fields();
+    if (exchange_mask) TRY(launch_slab_exchange(s, exchange_mask));
   }
   return SAYAL_OK;
 }
@@ -338,7 +348,7 @@ static int step_impl(Sim* s, const sayal_source* src, float d_t) {
       }
       int k = s->cfg.proj_n - done < D / 2 ? s->cfg.proj_n - done : D / 2;
       s->fuse_extrap = fold_extrap && done + k == s->cfg.proj_n;
-      TRY(projection(s, k, d_t));
+      if (!(skip & 16)) TRY(projection(s, k, d_t));
       D -= 2 * k;
       done += k;
     }
@@ -353,17 +363,21 @@ static int step_impl(Sim* s, const sayal_source* src, float d_t) {
     if (!(skip & 4)) TRY(advect_velocity(s, d_t));
     if (s->ph.enable_smoke && s->ph.wt_smoke != 0.f && !(skip & 8)) TRY(advect_smoke(s, d_t));  // decay fused (fluid.cu:792)
   } else {
-    const bool smoke = s->ph.enable_smoke && s->ph.wt_smoke != 0.f;
+    const bool smoke = s->ph.enable_smoke && s->ph.wt_smoke != 0.f && !(skip & 8);
+    const int end_mask = (skip & 32) ? 0 : (1 | 2);  // profiling only: leave the end-of-step exchange out
     // velocity is advected on the owned rows and one ghost row each side; its gathers reach advect_margin rows
     if (D < s->advect_margin + 1) {
       TRY(launch_slab_exchange(s, 1 | 2));
       D = s->slab_halo;
     }
     set_valid_depth(s, D);
-    int r = advect_linked(s, d_t, false, 1, smoke ? 0 : (1 | 2));
+    int r = (skip & 4) ? SAYAL_OK : advect_linked(s, d_t, false, 1, smoke ? 0 : end_mask);
     if (r == SAYAL_OK && smoke) {
-      // new velocity: exact on the owned rows +- 1; smoke ghosts: exact to the full halo since the last exchange
-      r = advect_linked(s, d_t, true, 0, 1 | 2 | 4);
+      // new velocity: exact on the owned rows +- 1; smoke ghosts: exact as deep as exchanges carry smoke
+      // (advect_margin + 2 rows, slab_exchange.cu) — a gather beyond that counts as halo overflow
+      const int smoke_depth = s->slab_halo < s->advect_margin + 2 ? s->slab_halo : s->advect_margin + 2;
+      set_valid_depth(s, D < smoke_depth ? D : smoke_depth);
+      r = advect_linked(s, d_t, true, 0, end_mask ? (end_mask | 4) : 0);
     }
     s->g.valid_lo = 0;
     s->g.valid_hi = s->g.local_rows;

@@ -45,35 +45,57 @@ __device__ __forceinline__ long long now_ns() {
 
 struct Fields3 {
   float* f[3];
+  int rows[3];  // edge rows of each field that travel: u, v to the full halo depth; smoke only as deep as the
+                // advection gathers (advect_margin + 2) — the projection never reads it
   int n;
 };
 
-// rows [row0, row0 + nrows) of every selected field <-> packed buffer [field][row][W]
+// `rows[f]` rows of every selected field <-> packed buffer [field][row][W].  The rows next to the slab edge on
+// `side` are the ones that travel: on the low side the range starts at `edge`, on the high side it ends there.
+// Four independent 16-byte loads are in flight per thread before the first store: the copy is latency bound
+// (local L2 read, then a posted NVLink write), not bandwidth bound.
 template <bool UNPACK>
-__device__ __forceinline__ void copy_rows(const Grid& g, const Fields3& fs, int row0, int nrows, float* buf, int block,
+__device__ __forceinline__ void copy_rows(const Grid& g, const Fields3& fs, int edge, bool ends_at_edge, float* buf, int block,
                                           int nblocks) {
   const int W = g.W;
-  const size_t per = (size_t)nrows * W;
-  if ((W & 3) == 0) {  // 16-byte path: pitch and W are multiples of 4, rows are 16-byte aligned on both sides
-    const int w4 = W >> 2;
-    const size_t per4 = (size_t)nrows * w4;
-    for (int f = 0; f < fs.n; f++) {
-      float4* b4 = reinterpret_cast<float4*>(buf + f * per);
-      for (size_t t = (size_t)block * XTHREADS + threadIdx.x; t < per4; t += (size_t)nblocks * XTHREADS) {
+  size_t base = 0;
+  for (int f = 0; f < fs.n; f++) {
+    const int nrows = fs.rows[f];
+    const int row0 = ends_at_edge ? edge - nrows : edge;
+    const size_t per = (size_t)nrows * W;
+    if ((W & 3) == 0) {  // 16-byte path: pitch and W are multiples of 4, rows are 16-byte aligned on both sides
+      const int w4 = W >> 2;
+      const size_t per4 = (size_t)nrows * w4, step = (size_t)nblocks * XTHREADS;
+      float4* b4 = reinterpret_cast<float4*>(buf + base);
+      float* field = fs.f[f] + (size_t)row0 * g.pitch;
+      auto cell = [&](size_t t) -> float4* {
         int row = (int)(t / w4), c = (int)(t - (size_t)row * w4);
-        float4* p = reinterpret_cast<float4*>(fs.f[f] + (size_t)(row0 + row) * g.pitch) + c;
-        if (UNPACK) *p = __ldcg(b4 + t);  // peer-written: read through L2, never a stale L1 line
-        else b4[t] = *p;
+        return reinterpret_cast<float4*>(field + (size_t)row * g.pitch) + c;
+      };
+      size_t t = (size_t)block * XTHREADS + threadIdx.x;
+      for (; t + 3 * step < per4; t += 4 * step) {
+        float4 v0, v1, v2, v3;
+        if (UNPACK) {  // peer-written: read through L2, never a stale L1 line
+          v0 = __ldcg(b4 + t); v1 = __ldcg(b4 + t + step); v2 = __ldcg(b4 + t + 2 * step); v3 = __ldcg(b4 + t + 3 * step);
+          *cell(t) = v0; *cell(t + step) = v1; *cell(t + 2 * step) = v2; *cell(t + 3 * step) = v3;
+        } else {
+          v0 = *cell(t); v1 = *cell(t + step); v2 = *cell(t + 2 * step); v3 = *cell(t + 3 * step);
+          b4[t] = v0; b4[t + step] = v1; b4[t + 2 * step] = v2; b4[t + 3 * step] = v3;
+        }
       }
-    }
-  } else {
-    for (int f = 0; f < fs.n; f++)
+      for (; t < per4; t += step) {
+        if (UNPACK) *cell(t) = __ldcg(b4 + t);
+        else b4[t] = *cell(t);
+      }
+    } else {
       for (size_t t = (size_t)block * XTHREADS + threadIdx.x; t < per; t += (size_t)nblocks * XTHREADS) {
         int row = (int)(t / W), c = (int)(t - (size_t)row * W);
         float* p = fs.f[f] + (size_t)(row0 + row) * g.pitch + c;
-        if (UNPACK) *p = __ldcg(buf + f * per + t);
-        else buf[f * per + t] = *p;
+        if (UNPACK) *p = __ldcg(buf + base + t);
+        else buf[base + t] = *p;
       }
+    }
+    base += per;
   }
 }
 
@@ -88,7 +110,7 @@ __global__ void __launch_bounds__(XTHREADS) slab_exchange_kernel(Grid g, int hal
   if (!d.peer_recv[side]) return;
   const unsigned seq = d.send_seq[side];  // == recv_seq: advanced below by the last CTA, after every CTA has read it
   float* dst = d.peer_recv[side] + (size_t)(seq & 1u) * d.stage_elems;
-  copy_rows<false>(g, fs, side == 0 ? g.own_lo : g.own_hi - halo, halo, dst, blockIdx.x, gridDim.x);
+  copy_rows<false>(g, fs, side == 0 ? g.own_lo : g.own_hi, side == 1, dst, blockIdx.x, gridDim.x);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();
@@ -108,7 +130,7 @@ __global__ void __launch_bounds__(XTHREADS) slab_exchange_kernel(Grid g, int hal
   }
   __syncthreads();
   const float* src = d.my_recv[side] + (size_t)(seq & 1u) * d.stage_elems;
-  copy_rows<true>(g, fs, side == 0 ? g.own_lo - halo : g.own_hi, halo, const_cast<float*>(src), blockIdx.x, gridDim.x);
+  copy_rows<true>(g, fs, side == 0 ? g.own_lo : g.own_hi, side == 0, const_cast<float*>(src), blockIdx.x, gridDim.x);
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned t = atomicAdd(&d.ticket[2 + side], 1u);
@@ -174,12 +196,14 @@ int launch_slab_exchange_on(Sim* s, int field_mask, cudaStream_t stream) {
   if (!s->link_block || (!d.peer_recv[0] && !d.peer_recv[1])) return SAYAL_OK;  // no neighbours: nothing to do
   Fields3 fs;
   fs.n = 0;
-  if (field_mask & 1) fs.f[fs.n++] = s->u;
-  if (field_mask & 2) fs.f[fs.n++] = s->v;
-  if (field_mask & 4) fs.f[fs.n++] = s->smoke;
+  const int smoke_rows = s->slab_halo < s->advect_margin + 2 ? s->slab_halo : s->advect_margin + 2;
+  if (field_mask & 1) { fs.rows[fs.n] = s->slab_halo; fs.f[fs.n++] = s->u; }
+  if (field_mask & 2) { fs.rows[fs.n] = s->slab_halo; fs.f[fs.n++] = s->v; }
+  if (field_mask & 4) { fs.rows[fs.n] = smoke_rows; fs.f[fs.n++] = s->smoke; }
   if (fs.n == 0) return set_error(SAYAL_EINVAL, "slab exchange: field_mask selects nothing");
-  for (int k = fs.n; k < 3; k++) fs.f[k] = fs.f[0];
-  size_t items = (size_t)s->slab_halo * s->g.W * fs.n / 4;
+  size_t items = 0;
+  for (int k = 0; k < fs.n; k++) items += (size_t)fs.rows[k] * s->g.W / 4;
+  for (int k = fs.n; k < 3; k++) { fs.f[k] = fs.f[0]; fs.rows[k] = 0; }
   int blocks = (int)((items + XTHREADS - 1) / XTHREADS);
   if (blocks < 1) blocks = 1;
   // at most 8 fat CTAs per side: the exchange shares the GPU with the interior tiles it overlaps with, and the
