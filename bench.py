@@ -95,7 +95,7 @@ class ClockSampler:
             self._stop.wait(self.period)
 
     def __enter__(self):
-        if self.nv:
+        if self.nv and not os.environ.get("SAYAL_BENCH_NO_SAMPLER"):
             self._thread = threading.Thread(target=self._run, daemon=True)
             self._thread.start()
         return self

@@ -367,25 +367,61 @@ def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSa
     stream = sf.slab.stream
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     warm = max(args.warmup, 3)
-    sf.run(warm)
+
+    def one_step(a=None, b=None):
+        with torch.cuda.stream(stream):
+            flush.fill_(1)
+        if a is not None:
+            a.record(stream)
+        sf.run(1)
+        if b is not None:
+            b.record(stream)
+
+    # warm-up runs the very loop body that is timed below: the first call of anything (torch's fill kernel, an
+    # event) loads code lazily and can stall a rank for milliseconds — which its neighbours would then book as a
+    # slow first step while they wait for its rows
+    for _ in range(warm):
+        one_step(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     sf.sync()
     dist.barrier()
     torch.cuda.synchronize()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    launches0 = sf.sim.launch_count
-    with ClockSampler(local) as clocks:
+    # Two untimed steps after the barrier: ranks leave a barrier up to ~0.1 ms apart, and the neighbours of a late
+    # rank would book that wait into their first timed steps.  The exchanges of these two steps line the ranks
+    # up on the device; the K timed steps follow back to back in the same queue.
+    import gc
+    gc.collect()
+    gc.disable()  # no collector pause in the enqueue loop
+    with ClockSampler(local, period=0.004) as clocks:  # started before the untimed steps: its first query is slow
+        one_step()
+        one_step()
+        launches0 = sf.sim.launch_count
         for k in range(args.steps):
-            with torch.cuda.stream(stream):
-                flush.fill_(1)
-            starts[k].record(stream)
-            sf.run(1)
-            stops[k].record(stream)
+            one_step(starts[k], stops[k])
         sf.sync()
         torch.cuda.synchronize()
         dist.barrier()
+    gc.enable()
     launches = sf.sim.launch_count - launches0
-    ms_local = sum(s.elapsed_time(e) for s, e in zip(starts, stops)) / args.steps
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    ms_local = sum(step_ms) / args.steps
+    mine = torch.tensor(step_ms, dtype=torch.float64, device="cuda")
+    every = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine)
+    every = torch.stack(every).cpu()          # [rank][step]
+    worst = every.max(dim=0).values           # slowest rank of every step
+    per_step = sorted(float(x) for x in worst)
+    k_bad = int(worst.argmax())
+    med = per_step[len(per_step) // 2]
+    slowest_step = {"index": k_bad, "ms": round(float(worst[k_bad]), 4),
+                    "ms_per_rank": [round(float(x), 3) for x in every[:, k_bad]]}
+    if os.environ.get("SAYAL_BENCH_DEBUG"):
+        import sys
+        gaps = [stops[k].elapsed_time(starts[k + 1]) for k in range(args.steps - 1)]
+        print(f"[rank {rank}] step ms: min {min(step_ms):.4f} med {sorted(step_ms)[len(step_ms) // 2]:.4f} max {max(step_ms):.4f}; "
+              f"flush gap ms: med {sorted(gaps)[len(gaps) // 2]:.4f} max {max(gaps):.4f}; first 8: {[round(x, 3) for x in step_ms[:8]]}",
+              file=sys.stderr, flush=True)
     t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
@@ -410,6 +446,10 @@ def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSa
     field_bytes = 3 * cells * 4
     launches_t = torch.tensor([launches], dtype=torch.int64, device="cuda")
     dist.all_reduce(launches_t, op=dist.ReduceOp.SUM)
+    plan_t = torch.tensor([sf.sim.get_option("plan_temporal_block"), sf.sim.get_option("plan_rows_per_warp"),
+                           sf.sim.get_option("local_rows")], dtype=torch.int64, device="cuda")
+    plans = [torch.zeros_like(plan_t) for _ in range(world)]
+    dist.all_gather(plans, plan_t)
     peak, peak_src = measured_hbm_peak()
     b_alg = algorithmic_bytes_per_cell_step(c.proj_n, int(bool(c.enable_pressure)), 1)
     line = None
@@ -420,7 +460,9 @@ def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSa
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_block(cfg, world, {"halo_rows": halo, "exchange": "peer-memory stores over NVLink from the library's kernels, graph-replayed step" if transport == "p2p"
                                                 else "NCCL send/recv of packed edge rows",
-                                                "halo_overflow": int(overflow[0])}),
+                                                "halo_overflow": int(overflow[0]),
+                                                "tile_plans_per_rank": [{"temporal_block": int(p[0]), "rows_per_warp": int(p[1]),
+                                                                         "local_rows": int(p[2])} for p in plans]}),
             "roofline": {"bound": "hbm", "kernel": "whole step, all GPUs", "achieved": round(value * b_alg / 1e9, 1),
                          "peak": peak * world, "unit": "GB/s", "frac": round(value * b_alg / 1e9 / (peak * world), 4),
                          "traffic": None, "peak_source": peak_src + f" x {world} GPUs"},
@@ -428,6 +470,9 @@ def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSa
             "e2e": {"value": e2e_value, "unit": "cell-steps/s", "h2d_bytes_per_step": field_bytes / args.steps + 20,
                     "d2h_bytes_per_step": field_bytes / args.steps},
             "gpu_launches": int(launches_t[0]), "clocks": clocks.summary(),
+            "step_ms_slowest_rank": {"min": round(per_step[0], 4), "median": round(per_step[len(per_step) // 2], 4),
+                                     "p90": round(per_step[int(0.9 * (len(per_step) - 1))], 4), "max": round(per_step[-1], 4),
+                                     "slowest_step": slowest_step},
         }
     sf.close()
     dist.barrier()
