@@ -12,7 +12,7 @@ value     whole-job throughput, state resident in HBM, every step timed on its o
           sim's stream and the L2 flushed (256 MiB write) between steps; max over ranks.
 e2e       the same job through the public API from pinned HOST buffers: upload u, v, smoke, K x step with a
           host-side Source, download u, v, smoke — wall clock, copies inside the timed region.
-roofline  the dominant kernel (projection_tile_kernel): algorithmic bytes per launch / mean launch duration
+roofline  the dominant kernel (projection_pack_kernel): algorithmic bytes per launch / mean launch duration
           (CUDA events around the projection stage), against MEASURED_PEAKS.json's HBM copy bandwidth.
 cpu_baseline  the CPU restatement (oracle/, "port") on one host core, bounded sample of the same workload.
 
@@ -195,7 +195,7 @@ def bench_ours_single(args):
     sim.sync()
     warm_ms = e0.elapsed_time(e1) / args.steps
 
-    # ---- dominant kernel: the projection stage alone (passes x projection_tile_kernel)
+    # ---- dominant kernel: the projection stage alone (passes x projection_pack_kernel)
     n = c.proj_n
     l0 = sim.launch_count
     sim.stage_projection(n, c.d_t)
@@ -215,8 +215,19 @@ def bench_ours_single(args):
     achieved = alg_bytes_launch / (launch_ms * 1e-3) / 1e9
     peak, peak_src = measured_hbm_peak()
     b_alg = algorithmic_bytes_per_cell_step(n, int(bool(c.enable_pressure)), int(bool(c.enable_smoke and c.wt_smoke != 0)))
-    roofline = {"bound": "hbm", "kernel": "projection_tile_kernel", "achieved": round(achieved, 1), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+    # physical DRAM bytes per launch of that kernel, from the committed ncu --set full capture of the same plan
+    traffic, traffic_src = None, None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            t = json.loads(tp.read_text())
+            if (t["temporal_block"], t["rows_per_warp"]) == (sim.get_option("plan_temporal_block"),
+                                                              sim.get_option("plan_rows_per_warp")):
+                traffic, traffic_src = t["dram_bytes_per_launch"], "profiles/traffic.json: " + t["source"]
+        except Exception:
+            pass
+    roofline = {"bound": "hbm", "kernel": "projection_pack_kernel", "achieved": round(achieved, 1), "peak": peak,
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "launches_per_step": passes, "ms_per_launch": round(launch_ms, 5),
                 "algorithmic_bytes_per_launch": alg_bytes_launch,
                 "share_of_step": round(proj_ms / ms_per_step, 3),

@@ -149,6 +149,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   s->use_graph = 1;
   s->use_pdl = 1;
   s->fuse_forces = 1;
+  s->fuse_extrapolation = 1;
   s->order_tiles = 1;
   s->advect_kernel = 2;
   s->overlap_exchange = 1;
@@ -169,6 +170,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   if (const char* e = getenv("SAYAL_USE_PDL")) s->use_pdl = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_FUSE_FORCES")) s->fuse_forces = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_ORDER_TILES")) s->order_tiles = atoi(e) != 0;
+  if (const char* e = getenv("SAYAL_FUSE_EXTRAPOLATION")) s->fuse_extrapolation = atoi(e) != 0;
 
   auto fail = [&](int code) {
     free_sim(s);
@@ -334,8 +336,8 @@ static int step_impl(Sim* s, const sayal_source* src, float d_t) {
   // of depth, an exchange restores D = halo.  Exchanges happen only when the next operation needs more depth
   // than is left, and once at the end of the step (u, v and smoke together).
   int D = s->slab_halo;
-  // the pass that ends the projection also applies the boundary extrapolation (fuse_forces covers both folds)
-  const bool fold_extrap = s->fuse_forces && s->projection_kernel == 1 && !s->ph.enable_pressure && s->cfg.proj_n > 0;
+  // the pass that ends the projection also applies the boundary extrapolation (option fuse_extrapolation)
+  const bool fold_extrap = s->fuse_extrapolation && s->projection_kernel == 1 && !s->ph.enable_pressure && s->cfg.proj_n > 0;
   s->fuse_extrap = 0;
   if (!linked) {
     s->fuse_extrap = fold_extrap && !(skip & 2);
@@ -806,6 +808,8 @@ int sayal_set_option(sayal_sim* sim, const char* key, int64_t value) {
     s->use_pdl = value != 0;
   } else if (!strcmp(key, "fuse_forces")) {
     s->fuse_forces = value != 0;
+  } else if (!strcmp(key, "fuse_extrapolation")) {
+    s->fuse_extrapolation = value != 0;
   } else if (!strcmp(key, "order_tiles")) {
     s->order_tiles = value != 0;
     s->plan_variant = -1, s->n_plans = 0;
@@ -834,6 +838,7 @@ int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value) {
   else if (!strcmp(key, "use_pdl")) *value = s->use_pdl;
   else if (!strcmp(key, "fuse_forces")) *value = s->fuse_forces;
   else if (!strcmp(key, "order_tiles")) *value = s->order_tiles;
+  else if (!strcmp(key, "fuse_extrapolation")) *value = s->fuse_extrapolation;
   else if (!strcmp(key, "advect_kernel")) *value = s->advect_kernel;
   else if (!strcmp(key, "autotune")) *value = s->autotune;
   else if (!strcmp(key, "plan_temporal_block")) *value = s->plan_variant >= 0 ? s->plan_T : 0;

@@ -101,6 +101,7 @@ struct Sim {
   int advect_kernel;      // 0 plain per-cell kernels, 1 shared-memory tiles, 2 direct with geometry words (cell_size 1)
   int use_pdl;            // programmatic dependent launch between projection passes
   int fuse_forces;        // option: fold the forces into the load of the step's first projection pass (default 1)
+  int fuse_extrapolation; // option: fold the boundary extrapolation into the store of the step's last projection pass (default 1)
   int fuse_pending;       // the step's forces have not been applied yet: the next tiled pass applies them
   ForceArgs fuse_args;
   int debug_skip;         // profiling only (option "debug_skip"): bit mask of step stages to leave out (wrong results!)

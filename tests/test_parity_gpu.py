@@ -199,7 +199,9 @@ def test_forces_folded_into_first_projection_pass(width, height):
     fused, cpu = pair(cfg)
     plain, _ = pair(cfg)
     plain.set_option("fuse_forces", 0)
-    assert fused.get_option("fuse_forces") == 1
+    plain.set_option("fuse_extrapolation", 0)
+    fused.set_option("fuse_forces", 1)
+    fused.set_option("fuse_extrapolation", 1)
     for step in range(3):
         l0, l1 = fused.launch_count, plain.launch_count
         fused.update(None, cfg.c.d_t)
