@@ -147,6 +147,8 @@ struct PackArgs {
   // the form it takes with no drag and no interactive source: v += g d_t everywhere, u = speed and smoke = value
   // on the inlet cells).  Tiles overlap, so a cell's forces are evaluated by every tile that loads it — the
   // same operation on the same input, hence the same bits — and the pass writes every cell exactly once.
+  float* p;              // pressure (PRESSURE variants): updated in place, see the kernel
+  float density, hf, inv_dt;  // update_pressure_at (fluid.cu:225-226): p += ((e * density) * cell_size) * (1 / d_t)
   int tiles_x;           // tiles per tile row (the grid is one-dimensional: blockIdx.x -> order -> tile)
   const int* order;      // tiles sorted by cost, most expensive first (tile_order_kernel), or null for row-major
   int extrap_on;  // the step's last pass: apply_extrapolation_at (fluid.cu:720-733) on the tile before it is stored
@@ -208,11 +210,24 @@ __device__ __forceinline__ long long globaltimer() {
 
 // One row of one half-sweep.  C = 0: columns (0,2) are the active colour, C = 1: columns (1,3).
 // vt / vb are the v faces above / below the row for the active columns.
-template <int C, bool MASKED>
-__device__ __forceinline__ void row_step(u64& U02, u64& U13, u64& vb, u64& vt, const Mult& m, u64 o2, int lane) {
+// pressure factors of one step, packed
+struct PMul {
+  u64 density, hf, inv_dt;
+};
+
+// update_pressure_at (fluid.cu:225-226) for the two cells just updated: p += ((e * density) * h) * (1 / d_t) as one
+// FMA, the pressure pair living in shared memory.  An inactive cell has e = +-0 and leaves its p unchanged.
+__device__ __forceinline__ void pressure_add(float* pp, u64 e, const PMul& pm) {
+  sts64(pp, fma2(mul2(mul2(e, pm.density), pm.hf), pm.inv_dt, lds64(pp)));
+}
+
+template <int C, bool MASKED, bool PRESSURE>
+__device__ __forceinline__ void row_step(u64& U02, u64& U13, u64& vb, u64& vt, const Mult& m, u64 o2, int lane, float* pp,
+                                         const PMul& pm) {
   if (C == 0) {
     u64 d = sub2(add2(sub2(U13, U02), vt), vb);
     u64 e = mul2(o2, mul2(d, m.inv));
+    if (PRESSURE) pressure_add(pp, e, pm);
     U02 = fma2(e, m.mL, U02);
     U13 = fma2(e, m.nR, U13);
     if (MASKED) {
@@ -228,6 +243,7 @@ __device__ __forceinline__ void row_step(u64& U02, u64& U13, u64& vb, u64& vt, c
     u64 uR = pk(hi(U02), un);
     u64 d = sub2(add2(sub2(uR, U13), vt), vb);
     u64 e = mul2(o2, mul2(d, m.inv));
+    if (PRESSURE) pressure_add(pp, e, pm);
     U13 = fma2(e, m.mL, U13);
     uR = fma2(e, m.nR, uR);
     if (MASKED) {
@@ -247,13 +263,15 @@ __device__ __forceinline__ void row_step(u64& U02, u64& U13, u64& vb, u64& vt, c
 // IRR = false: every row uses the lane's profile multipliers.  IRR = true (a warp with at least one row that
 // differs from the profile): every row fetches its multipliers from the table; s_off holds, per row, the two
 // cases' byte offsets into it (16 bits each).  No per-row branch either way.
-template <int RY, int Q0, bool IRR>
+template <int RY, int Q0, bool IRR, bool PRESSURE>
 __device__ __forceinline__ void half_sweep(u64 (&U02)[RY], u64 (&U13)[RY], u64 (&V02)[RY - 1], u64 (&V13)[RY - 1],
                                            const Mult (&prof)[2], u64 o2, int lane, float* sv_top, float* sv_bot,
-                                           const unsigned* s_off, const LutEntry* lut) {
+                                           const unsigned* s_off, const LutEntry* lut, float* sp_warp,
+                                           const PMul& pm) {
 #pragma unroll
   for (int r = 0; r < RY; r++) {
     const int c = Q0 ^ (r & 1);
+    float* pp = sp_warp + r * 128 + 64 * c;  // this lane's pressure pair of row r for the active colour
     u64 vt, vb;
     if (r == 0) vt = lds64(sv_top + 64 * c);
     else vt = c ? V13[r - 1] : V02[r - 1];
@@ -262,11 +280,11 @@ __device__ __forceinline__ void half_sweep(u64 (&U02)[RY], u64 (&U13)[RY], u64 (
     if (IRR) {
       unsigned word = s_off[r * 32];
       Mult m = lut_load(lut, c ? (word >> 16) : (word & 0xffffu));
-      if (c == 0) row_step<0, true>(U02[r], U13[r], vb, vt, m, o2, lane);
-      else row_step<1, true>(U02[r], U13[r], vb, vt, m, o2, lane);
+      if (c == 0) row_step<0, true, PRESSURE>(U02[r], U13[r], vb, vt, m, o2, lane, pp, pm);
+      else row_step<1, true, PRESSURE>(U02[r], U13[r], vb, vt, m, o2, lane, pp, pm);
     } else {
-      if (c == 0) row_step<0, false>(U02[r], U13[r], vb, vt, prof[0], o2, lane);
-      else row_step<1, false>(U02[r], U13[r], vb, vt, prof[1], o2, lane);
+      if (c == 0) row_step<0, false, PRESSURE>(U02[r], U13[r], vb, vt, prof[0], o2, lane, pp, pm);
+      else row_step<1, false, PRESSURE>(U02[r], U13[r], vb, vt, prof[1], o2, lane, pp, pm);
     }
     if (r == 0) sts64(sv_top + 64 * c, vt);
     else if (c) V13[r - 1] = vt;
@@ -280,8 +298,13 @@ __device__ __forceinline__ void half_sweep(u64 (&U02)[RY], u64 (&U13)[RY], u64 (
 // FORCES: the step's first pass, which also applies the external forces while loading (a separate instantiation,
 // so the other passes keep their register allocation).
 // EXTRAP: the step's last pass, which also applies the boundary extrapolation before storing.
-template <int RY, int NW, bool FORCES, bool EXTRAP>
+// PRESSURE (enable_pressure): the tile's pressure lives in dynamic shared memory (TH x 128 floats, packed like the v
+// rows) and accumulates one FMA per cell update.  p is updated IN PLACE in global memory: a cell's p is written
+// only by the tile that owns it, which read it when the pass began; what other tiles read in their halo never
+// leaves them, and nothing else depends on p.
+template <int RY, int NW, bool FORCES, bool EXTRAP, bool PRESSURE>
 __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a) {
+  extern __shared__ __align__(16) float sp[];  // PRESSURE only
   constexpr int TH = RY * NW;
   // shared v rows: sv[0] is the v row above the tile (read-only halo), sv[w+1] is the last row of warp w.
   // Layout per row: [columns (0,2): 64 floats][columns (1,3): 64 floats]; lane l owns float2 at 2l of each.
@@ -339,6 +362,20 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
       vlast13 = pk(vv.y, vv.w);
     }
     fl[r] = f;
+  }
+  float* sp_warp = sp + (size_t)(w * RY) * 128 + 2 * lane;
+  PMul pm;
+  pm.density = pk(a.density, a.density);
+  pm.hf = pk(a.hf, a.hf);
+  pm.inv_dt = pk(a.inv_dt, a.inv_dt);
+  if (PRESSURE) {
+#pragma unroll
+    for (int r = 0; r < RY; r++) {
+      float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col_ok && lr0 + r < g.local_rows) pv = *reinterpret_cast<const float4*>(a.p + (size_t)(lr0 + r) * g.pitch + x);
+      sts64(sp_warp + r * 128, pk(pv.x, pv.z));
+      sts64(sp_warp + r * 128 + 64, pk(pv.y, pv.w));
+    }
   }
   if (FORCES) {
     // Forces on the register tile, AFTER the loop above: anything with control flow between the loads would keep
@@ -444,28 +481,28 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   if (!irr) {
     for (int it = 0; it < a.iters; it++) {
       if (q == 0) {
-        half_sweep<RY, 0, false>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut);
+        half_sweep<RY, 0, false, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
         __syncthreads();
-        half_sweep<RY, 1, false>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut);
+        half_sweep<RY, 1, false, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
         __syncthreads();
       } else {
-        half_sweep<RY, 1, false>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut);
+        half_sweep<RY, 1, false, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
         __syncthreads();
-        half_sweep<RY, 0, false>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut);
+        half_sweep<RY, 0, false, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
         __syncthreads();
       }
     }
   } else {
     for (int it = 0; it < a.iters; it++) {
       if (q == 0) {
-        half_sweep<RY, 0, true>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut);
+        half_sweep<RY, 0, true, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
         __syncthreads();
-        half_sweep<RY, 1, true>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut);
+        half_sweep<RY, 1, true, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
         __syncthreads();
       } else {
-        half_sweep<RY, 1, true>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut);
+        half_sweep<RY, 1, true, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
         __syncthreads();
-        half_sweep<RY, 0, true>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut);
+        half_sweep<RY, 0, true, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
         __syncthreads();
       }
     }
@@ -546,6 +583,10 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
         u64 p02 = r < RY - 1 ? V02[r < RY - 1 ? r : 0] : vlast02;
         u64 p13 = r < RY - 1 ? V13[r < RY - 1 ? r : 0] : vlast13;
         *reinterpret_cast<float4*>(a.v_out + k) = make_float4(lo(p02), lo(p13), hi(p02), hi(p13));
+        if (PRESSURE) {
+          u64 q02 = lds64(sp_warp + r * 128), q13 = lds64(sp_warp + r * 128 + 64);
+          *reinterpret_cast<float4*>(a.p + k) = make_float4(lo(q02), lo(q13), hi(q02), hi(q13));
+        }
       }
     }
   }
@@ -605,11 +646,12 @@ __global__ void tile_order_kernel(const int* __restrict__ cost, int tiles, int* 
 
 struct Variant {
   int ry, nw;
-  void (*kernel[4])(PackArgs);  // indexed by (forces on load) | (extrapolation before store) << 1
+  void (*kernel[5])(PackArgs);  // indexed by (forces on load) | (extrapolation before store) << 1; [4] = with pressure
 };
-#define SAYAL_PACK_VARIANT(RY, NW)                                                                          \
-  {RY, NW, {projection_pack_kernel<RY, NW, false, false>, projection_pack_kernel<RY, NW, true, false>,     \
-            projection_pack_kernel<RY, NW, false, true>, projection_pack_kernel<RY, NW, true, true>}}
+#define SAYAL_PACK_VARIANT(RY, NW)                                                                                        \
+  {RY, NW, {projection_pack_kernel<RY, NW, false, false, false>, projection_pack_kernel<RY, NW, true, false, false>,     \
+            projection_pack_kernel<RY, NW, false, true, false>, projection_pack_kernel<RY, NW, true, true, false>,       \
+            projection_pack_kernel<RY, NW, false, false, true>}}
 const Variant kVariants[] = {SAYAL_PACK_VARIANT(8, 16), SAYAL_PACK_VARIANT(10, 16), SAYAL_PACK_VARIANT(12, 16)};
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kMaxT = 16;
@@ -645,18 +687,20 @@ double model_cost(const Grid& g, const Variant& v, int T, int n, int sms) {
   return (double)passes * waves * v.ry * (0.45 + 0.13 * T);
 }
 
+size_t pressure_smem(const Variant& v) { return (size_t)v.ry * v.nw * 128 * sizeof(float); }
+
 int launch_pass(Sim* s, const Variant& v, const PackArgs& a, dim3 grid, cudaStream_t stream) {
   cudaLaunchConfig_t lc = {};
   lc.gridDim = grid;
   lc.blockDim = dim3(v.nw * 32);
-  lc.dynamicSmemBytes = 0;
+  lc.dynamicSmemBytes = a.p ? pressure_smem(v) : 0;
   lc.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr;
   lc.numAttrs = s->use_pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&lc, v.kernel[(a.force_on ? 1 : 0) | (a.extrap_on ? 2 : 0)], a);
+  cudaError_t e = cudaLaunchKernelEx(&lc, a.p ? v.kernel[4] : v.kernel[(a.force_on ? 1 : 0) | (a.extrap_on ? 2 : 0)], a);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
     char m[256];
@@ -695,7 +739,7 @@ const int* tile_order(Sim* s, int variant, int it, const Geometry& q) {
   return buf;
 }
 
-int run_passes(Sim* s, int variant, int T, int iterations, bool with_forces = false, bool with_extrap = false) {
+int run_passes(Sim* s, int variant, int T, int iterations, float d_t, bool with_forces = false, bool with_extrap = false) {
   const Variant& v = kVariants[variant];
   // ceil(iterations / T) passes of nearly equal size (25 at T = 10 -> 9, 8, 8 rather than 10, 10, 5): the same
   // number of loads and stores, but narrower halos on every pass
@@ -719,6 +763,10 @@ int run_passes(Sim* s, int variant, int T, int iterations, bool with_forces = fa
     a.halo_y = q.halo_y;
     a.stride_x = q.stride_x;
     a.stride_y = q.stride_y;
+    a.p = s->ph.enable_pressure ? s->p : nullptr;
+    a.density = s->ph.density;
+    a.hf = (float)s->g.h;
+    a.inv_dt = 1.0f / d_t;
     a.extrap_on = with_extrap && pass == passes - 1;
     a.force_on = with_forces && done == 0;
     a.smoke = s->smoke;
@@ -754,9 +802,11 @@ int tiled_max_temporal_block() { return kMaxT; }
 // loaded when the sim is created.
 int tiled_preload() {
   for (int v = 0; v < kNumVariants; v++)
-    for (int m = 0; m < 4; m++) {
+    for (int m = 0; m < 5; m++) {
       cudaFuncAttributes fa;
       cudaError_t e = cudaFuncGetAttributes(&fa, kVariants[v].kernel[m]);
+      if (e == cudaSuccess && m == 4)
+        e = cudaFuncSetAttribute(kVariants[v].kernel[4], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pressure_smem(kVariants[v]));
       if (e != cudaSuccess) return set_error(SAYAL_ECUDA, cudaGetErrorString(e));
     }
   return SAYAL_OK;
@@ -766,7 +816,7 @@ int tiled_preload() {
 // with the wave-quantisation model, then time the best few on the live arrays (state saved and restored;
 // every candidate produces the same bits, so the choice never changes results).
 int tiled_prepare(Sim* s, int iterations) {
-  if (s->ph.enable_pressure || iterations <= 0) return SAYAL_OK;
+  if (iterations <= 0) return SAYAL_OK;
   for (int k = 0; k < s->n_plans; k++)
     if (s->plans[k].iterations == iterations) {  // slab runs alternate between chunk sizes: keep every plan
       s->plan_variant = s->plans[k].variant;
@@ -800,20 +850,23 @@ int tiled_prepare(Sim* s, int iterations) {
   int ntime = nc;
   if (s->autotune && cap == cudaStreamCaptureStatusNone && ntime > 1) {
     size_t bytes = sizeof(float) * (size_t)s->g.pitch * s->g.local_rows;
-    float *su = nullptr, *sv = nullptr;
-    if (cudaMalloc(&su, bytes) == cudaSuccess && cudaMalloc(&sv, bytes) == cudaSuccess) {
+    float *su = nullptr, *sv = nullptr, *spres = nullptr;  // the timed runs advance u, v (and accumulate into p)
+    const bool save_p = s->ph.enable_pressure;
+    if (cudaMalloc(&su, bytes) == cudaSuccess && cudaMalloc(&sv, bytes) == cudaSuccess &&
+        (!save_p || cudaMalloc(&spres, bytes) == cudaSuccess)) {
       cudaEvent_t e0, e1;
       cudaEventCreate(&e0);
       cudaEventCreate(&e1);
       cudaMemcpyAsync(su, s->u, bytes, cudaMemcpyDeviceToDevice, s->stream);
       cudaMemcpyAsync(sv, s->v, bytes, cudaMemcpyDeviceToDevice, s->stream);
+      if (save_p) cudaMemcpyAsync(spres, s->p, bytes, cudaMemcpyDeviceToDevice, s->stream);
       int64_t launches = s->launches;
       int parity = s->parity;
       float *u0 = s->u, *v0 = s->v, *ub0 = s->u_buf, *vb0 = s->v_buf;
       // one timed run of a candidate (ms), or a negative value on failure
       auto time_once = [&](const Cand& c) -> float {
         cudaEventRecord(e0, s->stream);
-        int r = run_passes(s, c.variant, c.T, iterations);
+        int r = run_passes(s, c.variant, c.T, iterations, 1.0f);
         cudaEventRecord(e1, s->stream);
         if (r != SAYAL_OK || cudaEventSynchronize(e1) != cudaSuccess) return -1.f;
         float ms = 0.f;
@@ -859,12 +912,14 @@ int tiled_prepare(Sim* s, int iterations) {
       s->launches = launches;
       cudaMemcpyAsync(s->u, su, bytes, cudaMemcpyDeviceToDevice, s->stream);
       cudaMemcpyAsync(s->v, sv, bytes, cudaMemcpyDeviceToDevice, s->stream);
+      if (save_p) cudaMemcpyAsync(s->p, spres, bytes, cudaMemcpyDeviceToDevice, s->stream);
       cudaStreamSynchronize(s->stream);
       cudaEventDestroy(e0);
       cudaEventDestroy(e1);
     }
     if (su) cudaFree(su);
     if (sv) cudaFree(sv);
+    if (spres) cudaFree(spres);
     cudaGetLastError();
   }
   s->plan_variant = cands[best].variant;
@@ -882,13 +937,12 @@ int tiled_prepare(Sim* s, int iterations) {
 }
 
 int launch_projection_tiled(Sim* s, int iterations, float d_t) {
-  if (s->ph.enable_pressure) return launch_projection_plain(s, iterations, d_t);  // pressure accumulates per cell: plain path
   int r = tiled_prepare(s, iterations);
   if (r != SAYAL_OK) return r;
   const bool with_forces = s->fuse_pending != 0, with_extrap = s->fuse_extrap != 0;
   s->fuse_pending = 0;
   s->fuse_extrap = with_extrap ? 2 : 0;  // 2 = done: the caller skips the extrapolation kernel
-  return run_passes(s, s->plan_variant, s->plan_T, iterations, with_forces, with_extrap);
+  return run_passes(s, s->plan_variant, s->plan_T, iterations, d_t, with_forces, with_extrap);
 }
 
 }  // namespace sayal

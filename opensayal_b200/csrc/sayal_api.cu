@@ -534,11 +534,13 @@ int sayal_get_field(sayal_sim* sim, int32_t field, void* host_dst) {
   size_t elem;
   bool dense;
   TRY(field_info(s, field, &p, &elem, &dense));
-  CUDA_TRY(cudaStreamSynchronize(s->stream));
   size_t src_pitch = (dense ? s->g.W : s->g.pitch) * elem;
   const char* src = (const char*)p + (size_t)s->g.own_lo * src_pitch;
-  CUDA_TRY(cudaMemcpy2D(host_dst, s->g.W * elem, src, src_pitch, s->g.W * elem, s->g.own_hi - s->g.own_lo,
-                        cudaMemcpyDeviceToHost));
+  const size_t row_bytes = s->g.W * elem, rows = s->g.own_hi - s->g.own_lo;
+  // in stream order behind the step that produced the field; one contiguous copy when rows are not padded
+  if (src_pitch == row_bytes) CUDA_TRY(cudaMemcpyAsync(host_dst, src, row_bytes * rows, cudaMemcpyDeviceToHost, s->stream));
+  else CUDA_TRY(cudaMemcpy2DAsync(host_dst, row_bytes, src, src_pitch, row_bytes, rows, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
   return SAYAL_OK;
 }
 
@@ -551,10 +553,13 @@ int sayal_set_field(sayal_sim* sim, int32_t field, const void* host_src) {
   size_t elem;
   bool dense;
   TRY(field_info(s, field, &p, &elem, &dense));
-  CUDA_TRY(cudaStreamSynchronize(s->stream));
   char* dst = (char*)p + (size_t)s->g.own_lo * s->g.pitch * elem;
-  CUDA_TRY(cudaMemcpy2D(dst, s->g.pitch * elem, host_src, s->g.W * elem, s->g.W * elem, s->g.own_hi - s->g.own_lo,
-                        cudaMemcpyHostToDevice));
+  const size_t row_bytes = s->g.W * elem, rows = s->g.own_hi - s->g.own_lo;
+  // In stream order: the copy waits for the steps already enqueued, later steps wait for it.  The host buffer
+  // may be reused when the call returns (pageable memory is staged by the runtime; for pinned memory we wait).
+  if (s->g.pitch * elem == row_bytes) CUDA_TRY(cudaMemcpyAsync(dst, host_src, row_bytes * rows, cudaMemcpyHostToDevice, s->stream));
+  else CUDA_TRY(cudaMemcpy2DAsync(dst, s->g.pitch * elem, host_src, row_bytes, row_bytes, rows, cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
   return SAYAL_OK;
 }
 

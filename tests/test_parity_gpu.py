@@ -119,6 +119,31 @@ def test_projection_with_pressure_and_range():
     assert (gpu.min_pressure, gpu.max_pressure) == cpu.pressure_range()
 
 
+@pytest.mark.parametrize("rows", [8, 10, 12])
+@pytest.mark.parametrize("T", [1, 3, 7, 16])
+def test_tiled_projection_accumulates_pressure(T, rows):
+    """enable_pressure on the tiled path: the tile's p lives in shared memory and takes one FMA per cell update
+    (fluid.cu:225-226); any tile plan == the plain half-sweep kernel == the oracle, bit for bit — two projections in
+    a row (p keeps accumulating across passes and calls), odd width, obstacle, d_t that is not a power of two."""
+    cfg = Config.defaults(333, 210, **{"fluid.viscosity": 0.0, "sim.enable_pressure": 1, "sim.physics.g": -5.0,
+                                       "sim.obstacle.radius": 21.0, "fluid.density": 1.3})
+    tiled, cpu = pair(cfg)
+    plain, _ = pair(cfg)
+    plain.set_option("projection_kernel", 0)
+    tiled.set_option("temporal_block", T)
+    tiled.set_option("tile_rows_per_warp", rows)
+    for f in (tiled, plain):
+        f.stage_zero_pressure()
+    cpu.zero_pressure()
+    for n, d_t in ((2 * T + 3, 0.03), (5, 0.07)):
+        tiled.stage_projection(n, d_t)
+        plain.stage_projection(n, d_t)
+        cpu.projection(n, d_t)
+    assert_same(tiled, cpu, names=("u", "v", "p"), what=f"tiled+pressure T={T} rows={rows}")
+    assert_same(plain, cpu, names=("u", "v", "p"), what="plain+pressure")
+    assert (tiled.min_pressure, tiled.max_pressure) == cpu.pressure_range()
+
+
 def test_extrapolation_bit_exact():
     cfg = CONFIGS["odd_203x157"]()
     gpu, cpu = pair(cfg)
