@@ -230,8 +230,11 @@ int sayal_path_lines(sayal_sim* sim, const sayal_visual* v, float d_t, int32_t* 
 
 /* Tuning / introspection.  set: "projection_kernel" (0 = plain half-sweeps, 1 = register-tile temporally
  * blocked), "temporal_block" (iterations per pass, 0 = choose), "tile_rows_per_warp" (0 = choose, 8/10/12),
- * "autotune" (time candidate tile plans on first use), "use_graph".  get: the same plus "plan_temporal_block",
- * "plan_rows_per_warp", "halo_overflow", "link_error", "pitch", "local_rows", "own_lo", "own_hi".  No option
+ * "autotune" (time candidate tile plans on first use), "use_graph", "use_pdl", "fuse_forces" / "fuse_extrapolation"
+ * (fold those stages into the first / last projection pass), "order_tiles" (issue expensive tiles first),
+ * "advect_kernel", "advect_margin", "overlap_exchange"; "debug_timeline" / "debug_skip" are profiling aids (the
+ * latter leaves stages out and does change results).  get: the same plus "plan_temporal_block",
+ * "plan_rows_per_warp", "halo_overflow", "link_error", "pitch", "local_rows", "own_lo", "own_hi".  No other option
  * changes results. */
 int sayal_set_option(sayal_sim* sim, const char* key, int64_t value);
 int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value);
@@ -255,14 +258,17 @@ int sayal_slab_unpack_ghost(sayal_sim* sim, int32_t side, int32_t nrows, int32_t
  * Each slab sim owns one neighbour-writable device block.  Processes trade its CUDA IPC handle once
  * (export on the owner, connect on the neighbour; `side` 0 = the neighbour holding the rows above mine in memory,
  * 1 = below); slabs living in one process connect directly.  Once a slab has a neighbour, sayal_step / sayal_run
- * run the whole slab schedule — projection in chunks of halo/2 iterations with an exchange of u, v after each,
- * exchanges after velocity and smoke advection — on the sim's stream, graph-captured by sayal_run.  The ranks
- * must issue the same sequence of steps. */
+ * run the whole slab schedule on the sim's stream, graph-captured by sayal_run: ghost rows lose two rows of
+ * validity per SOR iteration and are refreshed (u, v) only when the next operation needs more depth than is left,
+ * and once at the end of the step (u, v to the full halo, smoke advect_margin + 2 rows) under the interior smoke
+ * advection.  With halo >= 2 n + advect_margin + 2 a step has exactly one exchange.  The ranks must issue the same
+ * sequence of steps and use the same halo and advect_margin. */
 #define SAYAL_IPC_HANDLE_BYTES 64
 int sayal_slab_ipc_export(sayal_sim* sim, void* handle_out /* 64 bytes */, int64_t* stage_elems);
 int sayal_slab_ipc_connect(sayal_sim* sim, int32_t side, const void* handle /* 64 bytes */, int64_t stage_elems);
 int sayal_slab_connect_local(sayal_sim* sim, int32_t side, sayal_sim* neighbour);
-/* One exchange of the `halo` edge rows of the fields in field_mask (1 = U, 2 = V, 4 = SMOKE) with both neighbours. */
+/* One exchange of the edge rows of the fields in field_mask (1 = U, 2 = V: `halo` rows; 4 = SMOKE: advect_margin + 2
+ * rows) with both neighbours. */
 int sayal_slab_exchange(sayal_sim* sim, int32_t field_mask);
 
 const char* sayal_last_error(void);
