@@ -149,6 +149,12 @@ struct PackArgs {
   // same operation on the same input, hence the same bits — and the pass writes every cell exactly once.
   float* p;              // pressure (PRESSURE variants): updated in place, see the kernel
   float density, hf, inv_dt;  // update_pressure_at (fluid.cu:225-226): p += ((e * density) * cell_size) * (1 / d_t)
+  // Row window of this pass: local rows [row_lo, row_hi).  A whole domain passes (0, local_rows).  A linked slab
+  // passes its owned rows plus the ghost rows that are still exact: ghost rows lose two rows of validity per
+  // iteration, and sweeping rows that are already wrong is wasted work.  Rows outside the window are treated
+  // like rows outside the array (not loaded, never written); the window's outer edge behaves like a tile edge
+  // without a neighbour, which is what costs the next two rows per iteration.
+  int row_lo, row_hi;
   int tiles_x;           // tiles per tile row (the grid is one-dimensional: blockIdx.x -> order -> tile)
   const int* order;      // tiles sorted by cost, most expensive first (tile_order_kernel), or null for row-major
   int extrap_on;  // the step's last pass: apply_extrapolation_at (fluid.cu:720-733) on the tile before it is stored
@@ -319,7 +325,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   // computed once per tile geometry from the flags) and the open ones fill in behind them.
   const int tile = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
   const int tile_y = tile / a.tiles_x, tile_x = tile - tile_y * a.tiles_x;
-  const int X0 = tile_x * a.stride_x, Y0 = tile_y * a.stride_y;
+  const int X0 = tile_x * a.stride_x, Y0 = a.row_lo + tile_y * a.stride_y;
   const int x = X0 + 4 * lane;
   const int lr0 = Y0 + w * RY;
   long long* tl = a.timeline ? a.timeline + 5 * (size_t)tile : nullptr;
@@ -346,7 +352,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
     int lr = lr0 + r;
     float4 uu = make_float4(0.f, 0.f, 0.f, 0.f), vv = uu;
     unsigned f = 0;
-    if (col_ok && lr < g.local_rows) {
+    if (col_ok && lr < a.row_hi) {
       size_t k = (size_t)lr * g.pitch + x;
       uu = *reinterpret_cast<const float4*>(a.u_in + k);
       vv = *reinterpret_cast<const float4*>(a.v_in + k);
@@ -372,7 +378,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
 #pragma unroll
     for (int r = 0; r < RY; r++) {
       float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col_ok && lr0 + r < g.local_rows) pv = *reinterpret_cast<const float4*>(a.p + (size_t)(lr0 + r) * g.pitch + x);
+      if (col_ok && lr0 + r < a.row_hi) pv = *reinterpret_cast<const float4*>(a.p + (size_t)(lr0 + r) * g.pitch + x);
       sts64(sp_warp + r * 128, pk(pv.x, pv.z));
       sts64(sp_warp + r * 128 + 64, pk(pv.y, pv.w));
     }
@@ -384,7 +390,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
     const bool whole = x + 3 < g.W;  // the lane that straddles W updates only its real columns
 #pragma unroll
     for (int r = 0; r < RY; r++) {
-      if (!(col_ok && lr0 + r < g.local_rows)) continue;
+      if (!(col_ok && lr0 + r < a.row_hi)) continue;
       u64& p02 = r < RY - 1 ? V02[r < RY - 1 ? r : 0] : vlast02;
       u64& p13 = r < RY - 1 ? V13[r < RY - 1 ? r : 0] : vlast13;
       if (whole) {
@@ -401,7 +407,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
     if (x <= a.inlet_len) {  // inlet: u = speed, smoke = value; tiles overlap and every holder stores the same value
 #pragma unroll
       for (int r = 0; r < RY; r++) {
-        if (!(col_ok && lr0 + r < g.local_rows)) continue;
+        if (!(col_ok && lr0 + r < a.row_hi)) continue;
         float4 uu = make_float4(lo(U02[r]), lo(U13[r]), hi(U02[r]), hi(U13[r]));
         float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
         forces_on_load(a, x, lr0 + r, uu, vv);  // (only its inlet part matters here)
@@ -418,7 +424,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   }
   // The first row of a slab's local array has no row above it (its top faces are not held): carrier as well.
   // (On a whole domain that row is the top wall, already inactive.)
-  if (lr0 == 0) fl[0] = 0;
+  if (lr0 == a.row_lo) fl[0] = 0;
 
   // v faces above the tile's first row
   float* sv_top = &sv[w][2 * lane];
@@ -427,7 +433,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   sts64(sv_bot + 64, vlast13);
   if (w == 0) {
     float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (col_ok && Y0 >= 1 && Y0 - 1 < g.local_rows) {
+    if (col_ok && Y0 - 1 >= a.row_lo && Y0 - 1 < a.row_hi) {
       vv = *reinterpret_cast<const float4*>(a.v_in + (size_t)(Y0 - 1) * g.pitch + x);
       if (FORCES) {
         float4 unused = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -519,12 +525,12 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   if (EXTRAP) {
     const int lrA = g.H - 2 - g.row_base, lrB = lrA + 1;  // memory rows of j = 1 and j = 0
     // u(i, H-1) = u(i, H-2): memory rows 0 and 1, both rows of warp 0 of the top tiles
-    if (g.row_base == 0 && Y0 == 0 && w == 0 && g.local_rows >= 2) {
+    if (g.row_base == 0 && Y0 == 0 && w == 0 && a.row_hi >= 2) {
       U02[0] = U02[1];
       U13[0] = U13[1];
     }
     // u(i, 0) = u(i, 1): the two rows may sit in different warps, so row j = 1 travels through shared memory
-    if (lrA >= Y0 && lrA >= 0 && lrB < g.local_rows && lrB < Y0 + TH) {  // uniform over the CTA
+    if (lrA >= Y0 && lrA >= 0 && lrB < a.row_hi && lrB < Y0 + TH) {  // uniform over the CTA
       float4* scratch = reinterpret_cast<float4*>(&sv[0][0]);
 #pragma unroll
       for (int r = 0; r < RY; r++)
@@ -571,8 +577,8 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   // write the part of the tile that is exact: everything >= halo away from an edge that has a neighbour
   const int vx0 = X0 == 0 ? 0 : X0 + a.halo_x;
   const int vx1 = X0 + TW >= g.pitch ? g.pitch : X0 + TW - a.halo_x;
-  const int vy0 = Y0 == 0 ? 0 : Y0 + a.halo_y;
-  const int vy1 = Y0 + TH >= g.local_rows ? g.local_rows : Y0 + TH - a.halo_y;
+  const int vy0 = Y0 == a.row_lo ? a.row_lo : Y0 + a.halo_y;
+  const int vy1 = Y0 + TH >= a.row_hi ? a.row_hi : Y0 + TH - a.halo_y;
   if (x >= vx0 && x < vx1) {
 #pragma unroll
     for (int r = 0; r < RY; r++) {
@@ -600,16 +606,16 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
 // pack kernel: a row whose flags differ from the warp's middle row, or a middle row next to a horizontal
 // boundary).  One CTA per tile, thread layout as in the pack kernel.
 __global__ void tile_cost_kernel(Grid g, const uint8_t* __restrict__ flags, int ry, int stride_x, int stride_y, int tiles_x,
-                                 int* __restrict__ cost) {
+                                 int row_lo, int row_hi, int* __restrict__ cost) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int tile = blockIdx.x, tile_y = tile / tiles_x, tile_x = tile - tile_y * tiles_x;
-  const int x = tile_x * stride_x + 4 * lane, lr0 = tile_y * stride_y + w * ry;
+  const int x = tile_x * stride_x + 4 * lane, lr0 = row_lo + tile_y * stride_y + w * ry;
   auto flag_word = [&](int r) -> unsigned {
     int lr = lr0 + r;
     unsigned f = 0;
-    if (x < g.pitch && lr < g.local_rows) f = *reinterpret_cast<const unsigned*>(flags + (size_t)lr * g.pitch + x);
+    if (x < g.pitch && lr < row_hi) f = *reinterpret_cast<const unsigned*>(flags + (size_t)lr * g.pitch + x);
     if (lane == 31) f &= 0x00ffffffu;
-    if (lr == 0) f = 0;
+    if (lr == row_lo) f = 0;
     return f;
   };
   const unsigned pf = flag_word(ry / 2);
@@ -665,7 +671,8 @@ struct Geometry {
   int halo_x, halo_y, stride_x, stride_y, tiles_x, tiles_y;
 };
 
-bool geometry(const Grid& g, const Variant& v, int T, Geometry* out) {
+bool geometry(const Grid& g, const Variant& v, int T, Geometry* out, int rows = -1) {
+  if (rows < 0) rows = g.local_rows;
   int th = v.ry * v.nw;
   out->halo_y = 2 * T;
   out->halo_x = (2 * T + 3) & ~3;
@@ -673,7 +680,7 @@ bool geometry(const Grid& g, const Variant& v, int T, Geometry* out) {
   out->stride_y = th - 2 * out->halo_y;
   if (out->stride_x < TW / 4 || out->stride_y < th / 4) return false;  // keep at least a quarter of the tile useful
   out->tiles_x = tiles_for(g.pitch, TW, out->stride_x);
-  out->tiles_y = tiles_for(g.local_rows, th, out->stride_y);
+  out->tiles_y = tiles_for(rows, th, out->stride_y);
   return true;
 }
 
@@ -714,10 +721,12 @@ int launch_pass(Sim* s, const Variant& v, const PackArgs& a, dim3 grid, cudaStre
 // Device array with the tiles of geometry (variant, iterations-per-pass) in issue order; built on first use
 // (two small kernels on the sim's stream) and cached.  Returns null — row-major order — when the cache is full,
 // the option is off, or the stream is being captured and the geometry has not been seen before.
-const int* tile_order(Sim* s, int variant, int it, const Geometry& q) {
+const int* tile_order(Sim* s, int variant, int it, const Geometry& q, int row_lo, int row_hi) {
   if (!s->order_tiles) return nullptr;
   for (int k = 0; k < s->n_orders; k++)
-    if (s->orders[k].variant == variant && s->orders[k].it == it) return s->orders[k].order;
+    if (s->orders[k].variant == variant && s->orders[k].it == it && s->orders[k].row_lo == row_lo &&
+        s->orders[k].row_hi == row_hi)
+      return s->orders[k].order;
   const int tiles = q.tiles_x * q.tiles_y;
   if (s->n_orders == Sim::kMaxOrders || tiles <= 1) return nullptr;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -729,17 +738,19 @@ const int* tile_order(Sim* s, int variant, int it, const Geometry& q) {
     return nullptr;
   }
   const Variant& v = kVariants[variant];
-  tile_cost_kernel<<<tiles, v.nw * 32, 0, s->stream>>>(s->g, s->flags, v.ry, q.stride_x, q.stride_y, q.tiles_x, buf + tiles);
+  tile_cost_kernel<<<tiles, v.nw * 32, 0, s->stream>>>(s->g, s->flags, v.ry, q.stride_x, q.stride_y, q.tiles_x, row_lo, row_hi,
+                                                      buf + tiles);
   tile_order_kernel<<<1, 1024, 0, s->stream>>>(buf + tiles, tiles, buf);
   if (cudaGetLastError() != cudaSuccess) {
     cudaFree(buf);
     return nullptr;
   }
-  s->orders[s->n_orders++] = {variant, it, buf};
+  s->orders[s->n_orders++] = {variant, it, row_lo, row_hi, buf};
   return buf;
 }
 
-int run_passes(Sim* s, int variant, int T, int iterations, float d_t, bool with_forces = false, bool with_extrap = false) {
+int run_passes(Sim* s, int variant, int T, int iterations, float d_t, bool with_forces = false, bool with_extrap = false,
+               int ghost_depth = -1) {
   const Variant& v = kVariants[variant];
   // ceil(iterations / T) passes of nearly equal size (25 at T = 10 -> 9, 8, 8 rather than 10, 10, 5): the same
   // number of loads and stores, but narrower halos on every pass
@@ -748,10 +759,19 @@ int run_passes(Sim* s, int variant, int T, int iterations, float d_t, bool with_
   int done = 0;
   for (int pass = 0; pass < passes; pass++) {
     int it = base + (pass < longer ? 1 : 0);
+    // row window: everything, or (linked slab) the owned rows plus the ghost rows still exact before this pass
+    int row_lo = 0, row_hi = s->g.local_rows;
+    if (ghost_depth >= 0) {
+      const int depth = ghost_depth - 2 * done;
+      row_lo = s->g.own_lo - depth < 0 ? 0 : s->g.own_lo - depth;
+      row_hi = s->g.own_hi + depth > s->g.local_rows ? s->g.local_rows : s->g.own_hi + depth;
+    }
     Geometry q;
-    if (!geometry(s->g, v, it, &q)) return set_error(SAYAL_EINVAL, "projection tile: temporal block too large for the tile");
+    if (!geometry(s->g, v, it, &q, row_hi - row_lo)) return set_error(SAYAL_EINVAL, "projection tile: temporal block too large for the tile");
     PackArgs a;
     a.g = s->g;
+    a.row_lo = row_lo;
+    a.row_hi = row_hi;
     a.u_in = s->u;
     a.v_in = s->v;
     a.u_out = s->u_buf;
@@ -782,7 +802,7 @@ int run_passes(Sim* s, int variant, int T, int iterations, float d_t, bool with_
     if (s->d_timeline && (size_t)q.tiles_x * q.tiles_y * 5 > s->timeline_cap) a.timeline = nullptr;
     s->timeline_tiles = a.timeline ? q.tiles_x * q.tiles_y : 0;
     a.tiles_x = q.tiles_x;
-    a.order = tile_order(s, variant, it, q);
+    a.order = tile_order(s, variant, it, q, row_lo, row_hi);
     int r = launch_pass(s, v, a, dim3(q.tiles_x * q.tiles_y), s->stream);
     if (r != SAYAL_OK) return r;
     float* t = s->u; s->u = s->u_buf; s->u_buf = t;  // ping-pong: neighbouring tiles still read the old halo
@@ -928,11 +948,32 @@ int tiled_prepare(Sim* s, int iterations) {
     const int passes = (iterations + s->plan_T - 1) / s->plan_T;
     for (int it = iterations / passes; it <= (iterations + passes - 1) / passes; it++) {
       Geometry q;
-      if (it > 0 && geometry(s->g, kVariants[s->plan_variant], it, &q)) tile_order(s, s->plan_variant, it, q);
+      if (it > 0 && geometry(s->g, kVariants[s->plan_variant], it, &q)) tile_order(s, s->plan_variant, it, q, 0, s->g.local_rows);
     }
   }
   if (s->n_plans == Sim::kMaxPlans) s->n_plans = 0;  // full: start over (never happens with <= 8 chunk sizes)
   s->plans[s->n_plans++] = {iterations, s->plan_variant, s->plan_T};
+  return SAYAL_OK;
+}
+
+// Build (outside graph capture) the tile issue orders a linked slab's projection call of `iterations` iterations
+// will use when `ghost_depth` ghost rows are exact at its start: the same pass / window arithmetic as run_passes.
+int tiled_prepare_windows(Sim* s, int iterations, int ghost_depth) {
+  int r = tiled_prepare(s, iterations);
+  if (r != SAYAL_OK || iterations <= 0 || ghost_depth < 0) return r;
+  const Variant& v = kVariants[s->plan_variant];
+  const int passes = (iterations + s->plan_T - 1) / s->plan_T;
+  const int base = iterations / passes, longer = iterations % passes;
+  int done = 0;
+  for (int pass = 0; pass < passes; pass++) {
+    const int it = base + (pass < longer ? 1 : 0);
+    const int depth = ghost_depth - 2 * done;
+    const int row_lo = s->g.own_lo - depth < 0 ? 0 : s->g.own_lo - depth;
+    const int row_hi = s->g.own_hi + depth > s->g.local_rows ? s->g.local_rows : s->g.own_hi + depth;
+    Geometry q;
+    if (geometry(s->g, v, it, &q, row_hi - row_lo)) tile_order(s, s->plan_variant, it, q, row_lo, row_hi);
+    done += it;
+  }
   return SAYAL_OK;
 }
 
@@ -942,7 +983,9 @@ int launch_projection_tiled(Sim* s, int iterations, float d_t) {
   const bool with_forces = s->fuse_pending != 0, with_extrap = s->fuse_extrap != 0;
   s->fuse_pending = 0;
   s->fuse_extrap = with_extrap ? 2 : 0;  // 2 = done: the caller skips the extrapolation kernel
-  return run_passes(s, s->plan_variant, s->plan_T, iterations, d_t, with_forces, with_extrap);
+  const int depth = s->proj_depth;
+  s->proj_depth = -1;
+  return run_passes(s, s->plan_variant, s->plan_T, iterations, d_t, with_forces, with_extrap, depth);
 }
 
 }  // namespace sayal

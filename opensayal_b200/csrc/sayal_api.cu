@@ -150,6 +150,8 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   s->use_pdl = 1;
   s->fuse_forces = 1;
   s->fuse_extrapolation = 1;
+  s->shrink_window = 1;
+  s->proj_depth = -1;
   s->order_tiles = 1;
   s->advect_kernel = 2;
   s->overlap_exchange = 1;
@@ -170,6 +172,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   if (const char* e = getenv("SAYAL_USE_PDL")) s->use_pdl = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_FUSE_FORCES")) s->fuse_forces = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_ORDER_TILES")) s->order_tiles = atoi(e) != 0;
+  if (const char* e = getenv("SAYAL_SHRINK_WINDOW")) s->shrink_window = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_FUSE_EXTRAPOLATION")) s->fuse_extrapolation = atoi(e) != 0;
 
   auto fail = [&](int code) {
@@ -350,7 +353,9 @@ static int step_impl(Sim* s, const sayal_source* src, float d_t) {
       }
       int k = s->cfg.proj_n - done < D / 2 ? s->cfg.proj_n - done : D / 2;
       s->fuse_extrap = fold_extrap && done + k == s->cfg.proj_n;
+      s->proj_depth = s->shrink_window ? D : -1;  // sweep only the ghost rows that are still exact (projection_pack.cu)
       if (!(skip & 16)) TRY(projection(s, k, d_t));
+      s->proj_depth = -1;
       D -= 2 * k;
       done += k;
     }
@@ -450,7 +455,7 @@ int sayal_run(sayal_sim* sim, int32_t steps, float d_t) {
       for (int done = 0; done < s->cfg.proj_n;) {  // the chunk sizes step_impl will use
         if (D < 2) D = s->slab_halo;
         int k = s->cfg.proj_n - done < D / 2 ? s->cfg.proj_n - done : D / 2;
-        TRY(tiled_prepare(s, k));
+        TRY(tiled_prepare_windows(s, k, s->shrink_window ? D : -1));
         D -= 2 * k;
         done += k;
       }
@@ -815,6 +820,8 @@ int sayal_set_option(sayal_sim* sim, const char* key, int64_t value) {
     s->fuse_forces = value != 0;
   } else if (!strcmp(key, "fuse_extrapolation")) {
     s->fuse_extrapolation = value != 0;
+  } else if (!strcmp(key, "shrink_window")) {
+    s->shrink_window = value != 0;
   } else if (!strcmp(key, "order_tiles")) {
     s->order_tiles = value != 0;
     s->plan_variant = -1, s->n_plans = 0;
@@ -843,6 +850,7 @@ int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value) {
   else if (!strcmp(key, "use_pdl")) *value = s->use_pdl;
   else if (!strcmp(key, "fuse_forces")) *value = s->fuse_forces;
   else if (!strcmp(key, "order_tiles")) *value = s->order_tiles;
+  else if (!strcmp(key, "shrink_window")) *value = s->shrink_window;
   else if (!strcmp(key, "fuse_extrapolation")) *value = s->fuse_extrapolation;
   else if (!strcmp(key, "advect_kernel")) *value = s->advect_kernel;
   else if (!strcmp(key, "autotune")) *value = s->autotune;

@@ -104,6 +104,8 @@ struct Sim {
   int fuse_extrapolation; // option: fold the boundary extrapolation into the store of the step's last projection pass (default 1)
   int fuse_pending;       // the step's forces have not been applied yet: the next tiled pass applies them
   ForceArgs fuse_args;
+  int shrink_window;      // option: linked slabs sweep only the ghost rows that are still exact (default 1)
+  int proj_depth;         // linked slabs: ghost rows still exact when the next projection call starts (-1: all rows)
   int debug_skip;         // profiling only (option "debug_skip"): bit mask of step stages to leave out (wrong results!)
   int fuse_extrap;        // 1: the next tiled projection call ends the step's projection and also extrapolates; 2: it did
   int autotune;           // time candidate tile plans on first use
@@ -115,7 +117,7 @@ struct Sim {
   // issue order of the tiles (most expensive first) per tile geometry, built on first use (projection_pack.cu)
   int order_tiles;        // option (default 1)
   static constexpr int kMaxOrders = 64;
-  struct TileOrder { int variant, it; int* order; } orders[kMaxOrders];
+  struct TileOrder { int variant, it, row_lo, row_hi; int* order; } orders[kMaxOrders];
   int n_orders;
   // CUDA graph cache for sayal_run: one single-step graph per starting buffer parity, with the
   // pointer assignment the step leaves behind (the step swaps front and back buffers)
@@ -184,6 +186,7 @@ int launch_projection_tiled(Sim* s, int iterations, float d_t);
 int tiled_max_temporal_block();
 int tiled_preload();  // load every kernel variant now (never lazily in the middle of a linked step)
 int tiled_prepare(Sim* s, int iterations);  // choose the tile plan (may time candidates; not capturable)
+int tiled_prepare_windows(Sim* s, int iterations, int ghost_depth);  // + the issue orders of a linked slab's row windows
 
 
 }  // namespace sayal
