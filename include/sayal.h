@@ -241,6 +241,9 @@ int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value);
 /* Profiling only (option "debug_timeline" = 1): per-CTA timestamps of the last projection pass, 5 int64 per tile
  * {entry, tile loaded, sweeps done, stores issued (globaltimer ns), SM id}. */
 int sayal_debug_timeline(sayal_sim* sim, int64_t* host_dst, int32_t max_tiles, int32_t* n_tiles);
+/* Measurement aid: hold the sim's stream for `microseconds` (<= 1e6) with a one-thread spin kernel, so that a whole
+ * timed region can be enqueued before the device starts on it (host launch jitter then cannot drain the queue). */
+int sayal_stream_delay(sayal_sim* sim, int64_t microseconds);
 /* Number of kernels this library has launched on behalf of `sim` since creation. */
 int64_t sayal_launch_count(sayal_sim* sim);
 /* CUDA stream of the sim (cudaStream_t as void*), for event timing by the caller. */

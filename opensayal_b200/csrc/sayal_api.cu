@@ -891,6 +891,25 @@ int sayal_debug_timeline(sayal_sim* sim, int64_t* host_dst, int32_t max_tiles, i
   return SAYAL_OK;
 }
 
+// Measurement aid: hold the sim's stream for `microseconds` (one thread spinning on %globaltimer), so that a caller
+// can enqueue a whole timed region before the device starts on it and host jitter cannot drain the queue.
+__global__ void stream_delay_kernel(long long ns) {
+  long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  } while (t - t0 < ns);
+}
+
+int sayal_stream_delay(sayal_sim* sim, int64_t microseconds) {
+  if (!sim || microseconds < 0 || microseconds > 1000000) return set_error(SAYAL_EINVAL, "sayal_stream_delay: 0..1e6 us");
+  Sim* s = S(sim);
+  CUDA_TRY(cudaSetDevice(s->device));
+  stream_delay_kernel<<<1, 1, 0, s->stream>>>(microseconds * 1000);
+  CUDA_TRY(cudaGetLastError());
+  return SAYAL_OK;
+}
+
 int64_t sayal_launch_count(sayal_sim* sim) { return sim ? S(sim)->launches : 0; }
 void* sayal_stream(sayal_sim* sim) { return sim ? (void*)S(sim)->stream : nullptr; }
 

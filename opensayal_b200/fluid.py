@@ -351,6 +351,10 @@ class Fluid:
         check(self._lib.sayal_debug_timeline(self._sim, out.ctypes.data_as(C.c_void_p), max_tiles, C.byref(n)))
         return out[: n.value]
 
+    def stream_delay(self, microseconds: int) -> None:
+        """Measurement aid: hold the sim's stream so that a timed region can be enqueued ahead of the device."""
+        check(self._lib.sayal_stream_delay(self._sim, int(microseconds)))
+
     @property
     def launch_count(self) -> int:
         return self._lib.sayal_launch_count(self._sim)

@@ -394,6 +394,10 @@ def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSa
     gc.collect()
     gc.disable()  # no collector pause in the enqueue loop
     with ClockSampler(local, period=0.004) as clocks:  # started before the untimed steps: its first query is slow
+        # Hold the stream while the host enqueues the whole region (about 0.15 ms of host time per step): a rank whose
+        # host thread stalls for a few milliseconds would otherwise drain its queue, and its neighbours would book
+        # the wait for its rows as a slow step (seen at 8 ranks: one 3.5 ms step in fifty).
+        sf.sim.stream_delay(min(200000, 2000 + 400 * args.steps))
         one_step()
         one_step()
         launches0 = sf.sim.launch_count
