@@ -244,6 +244,15 @@ int sayal_debug_timeline(sayal_sim* sim, int64_t* host_dst, int32_t max_tiles, i
 /* Measurement aid: hold the sim's stream for `microseconds` (<= 1e6) with a one-thread spin kernel, so that a whole
  * timed region can be enqueued before the device starts on it (host launch jitter then cannot drain the queue). */
 int sayal_stream_delay(sayal_sim* sim, int64_t microseconds);
+/* Host-only introspection (no CUDA call, no sim): the passes the tiled projection takes for `iterations` iterations
+ * with temporal block T on an array of `pitch` x `local_rows` cells whose rows [own_lo, own_hi) are owned; ghost_depth
+ * < 0: every pass sweeps all rows, else pass k sweeps the owned rows +- (ghost_depth - 2 * iterations done before it).
+ * Per pass 11 int32: iterations, row_lo, row_hi, halo_x, halo_y, stride_x, stride_y, tiles_x, tiles_y, tile_w, tile_h.
+ * Tile (a, b) covers columns [a stride_x, +tile_w) and rows [row_lo + b stride_y, +tile_h) and writes the part that
+ * is at least a halo away from every edge that has a neighbouring tile. */
+int sayal_debug_pass_plans(int32_t pitch, int32_t local_rows, int32_t own_lo, int32_t own_hi, int32_t rows_per_warp,
+                           int32_t temporal_block, int32_t iterations, int32_t ghost_depth, int32_t* out,
+                           int32_t capacity, int32_t* n_passes);
 /* Number of kernels this library has launched on behalf of `sim` since creation. */
 int64_t sayal_launch_count(sayal_sim* sim);
 /* CUDA stream of the sim (cudaStream_t as void*), for event timing by the caller. */

@@ -151,6 +151,7 @@ SYMBOLS = [
     ("sayal_get_option", C.c_int, [_simp, C.c_char_p, C.POINTER(C.c_int64)]),
     ("sayal_debug_timeline", C.c_int, [_simp, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     ("sayal_stream_delay", C.c_int, [_simp, C.c_int64]),
+    ("sayal_debug_pass_plans", C.c_int, [C.c_int32] * 8 + [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
     ("sayal_launch_count", C.c_int64, [_simp]),
     ("sayal_stream", C.c_void_p, [_simp]),
     ("sayal_slab_pack_edge", C.c_int, [_simp, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

@@ -956,25 +956,67 @@ int tiled_prepare(Sim* s, int iterations) {
   return SAYAL_OK;
 }
 
+// The passes of one projection call: ceil(iterations / T) passes of nearly equal size; pass k sweeps the rows that
+// are still exact when it starts (everything when ghost_depth < 0).  run_passes evaluates the same arithmetic
+// pass by pass; this list form serves the order cache and sayal_debug_pass_plans (the CPU tests of the covering
+// invariants).
+struct PassPlan {
+  int iterations, row_lo, row_hi;
+  Geometry q;
+};
+
+int make_pass_plans(const Grid& g, const Variant& v, int T, int iterations, int ghost_depth, PassPlan* out, int capacity) {
+  if (iterations <= 0 || T <= 0) return 0;
+  const int passes = (iterations + T - 1) / T;
+  const int base = iterations / passes, longer = iterations % passes;
+  int done = 0, n = 0;
+  for (int pass = 0; pass < passes && n < capacity; pass++) {
+    PassPlan p;
+    p.iterations = base + (pass < longer ? 1 : 0);
+    p.row_lo = 0;
+    p.row_hi = g.local_rows;
+    if (ghost_depth >= 0) {
+      const int depth = ghost_depth - 2 * done;
+      p.row_lo = g.own_lo - depth < 0 ? 0 : g.own_lo - depth;
+      p.row_hi = g.own_hi + depth > g.local_rows ? g.local_rows : g.own_hi + depth;
+    }
+    if (!geometry(g, v, p.iterations, &p.q, p.row_hi - p.row_lo)) return -1;
+    out[n++] = p;
+    done += p.iterations;
+  }
+  return n;
+}
+
 // Build (outside graph capture) the tile issue orders a linked slab's projection call of `iterations` iterations
 // will use when `ghost_depth` ghost rows are exact at its start: the same pass / window arithmetic as run_passes.
 int tiled_prepare_windows(Sim* s, int iterations, int ghost_depth) {
   int r = tiled_prepare(s, iterations);
   if (r != SAYAL_OK || iterations <= 0 || ghost_depth < 0) return r;
-  const Variant& v = kVariants[s->plan_variant];
-  const int passes = (iterations + s->plan_T - 1) / s->plan_T;
-  const int base = iterations / passes, longer = iterations % passes;
-  int done = 0;
-  for (int pass = 0; pass < passes; pass++) {
-    const int it = base + (pass < longer ? 1 : 0);
-    const int depth = ghost_depth - 2 * done;
-    const int row_lo = s->g.own_lo - depth < 0 ? 0 : s->g.own_lo - depth;
-    const int row_hi = s->g.own_hi + depth > s->g.local_rows ? s->g.local_rows : s->g.own_hi + depth;
-    Geometry q;
-    if (geometry(s->g, v, it, &q, row_hi - row_lo)) tile_order(s, s->plan_variant, it, q, row_lo, row_hi);
-    done += it;
-  }
+  PassPlan plans[64];
+  const int n = make_pass_plans(s->g, kVariants[s->plan_variant], s->plan_T, iterations, ghost_depth, plans, 64);
+  for (int k = 0; k < n; k++) tile_order(s, s->plan_variant, plans[k].iterations, plans[k].q, plans[k].row_lo, plans[k].row_hi);
   return SAYAL_OK;
+}
+
+// Host-only (no CUDA call): the pass list of a projection on a grid described by numbers, for sayal_debug_pass_plans.
+int tiled_debug_pass_plans(int pitch, int local_rows, int own_lo, int own_hi, int rows_per_warp, int T, int iterations,
+                           int ghost_depth, int32_t* out, int capacity) {
+  int variant = -1;
+  for (int v = 0; v < kNumVariants; v++)
+    if (kVariants[v].ry == rows_per_warp) variant = v;
+  if (variant < 0 || pitch < 4 || (pitch & 3) || local_rows < 1 || T < 1 || T > kMaxT || own_lo < 0 || own_hi > local_rows)
+    return -1;
+  Grid g = {};
+  g.W = pitch; g.H = local_rows; g.pitch = pitch; g.local_rows = local_rows; g.own_lo = own_lo; g.own_hi = own_hi; g.h = 1;
+  PassPlan plans[64];
+  const int n = make_pass_plans(g, kVariants[variant], T, iterations, ghost_depth, plans, capacity < 64 ? capacity : 64);
+  for (int k = 0; k < n; k++) {
+    const PassPlan& p = plans[k];
+    const int32_t row[11] = {p.iterations, p.row_lo, p.row_hi, p.q.halo_x, p.q.halo_y, p.q.stride_x, p.q.stride_y,
+                             p.q.tiles_x, p.q.tiles_y, TW, kVariants[variant].ry * kVariants[variant].nw};
+    for (int c = 0; c < 11; c++) out[11 * k + c] = row[c];
+  }
+  return n;
 }
 
 int launch_projection_tiled(Sim* s, int iterations, float d_t) {

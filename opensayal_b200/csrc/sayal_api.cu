@@ -910,6 +910,17 @@ int sayal_stream_delay(sayal_sim* sim, int64_t microseconds) {
   return SAYAL_OK;
 }
 
+int sayal_debug_pass_plans(int32_t pitch, int32_t local_rows, int32_t own_lo, int32_t own_hi, int32_t rows_per_warp,
+                           int32_t temporal_block, int32_t iterations, int32_t ghost_depth, int32_t* out, int32_t capacity,
+                           int32_t* n_passes) {
+  if (!out || !n_passes || capacity < 1) return set_error(SAYAL_EINVAL, "sayal_debug_pass_plans: null argument");
+  int n = tiled_debug_pass_plans(pitch, local_rows, own_lo, own_hi, rows_per_warp, temporal_block, iterations, ghost_depth,
+                                 out, capacity);
+  if (n < 0) return set_error(SAYAL_EINVAL, "sayal_debug_pass_plans: no such plan (rows per warp 8/10/12, T 1..16, pitch % 4 == 0)");
+  *n_passes = n;
+  return SAYAL_OK;
+}
+
 int64_t sayal_launch_count(sayal_sim* sim) { return sim ? S(sim)->launches : 0; }
 void* sayal_stream(sayal_sim* sim) { return sim ? (void*)S(sim)->stream : nullptr; }
 

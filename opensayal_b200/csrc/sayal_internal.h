@@ -184,6 +184,8 @@ int launch_arrows(Sim* s, const sayal_visual* v, int nx, int ny, sayal_arrow* d_
 // ---- projection_pack.cu --------------------------------------------------------------------------
 int launch_projection_tiled(Sim* s, int iterations, float d_t);
 int tiled_max_temporal_block();
+int tiled_debug_pass_plans(int pitch, int local_rows, int own_lo, int own_hi, int rows_per_warp, int T, int iterations,
+                           int ghost_depth, int32_t* out, int capacity);  // host only; 11 int32 per pass, see sayal.h
 int tiled_preload();  // load every kernel variant now (never lazily in the middle of a linked step)
 int tiled_prepare(Sim* s, int iterations);  // choose the tile plan (may time candidates; not capturable)
 int tiled_prepare_windows(Sim* s, int iterations, int ghost_depth);  // + the issue orders of a linked slab's row windows
