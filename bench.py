@@ -175,7 +175,7 @@ def bench_ours_single(args):
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     launches0 = sim.launch_count
-    with ClockSampler(0) as clocks:
+    with ClockSampler(0, period=0.004) as clocks:  # several samples inside a region of a few milliseconds
         sim.stream_delay(min(200000, 2000 + 400 * args.steps))  # the host enqueues the region ahead of the device
         for k in range(args.steps):
             flush_l2()
