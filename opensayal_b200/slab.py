@@ -64,7 +64,8 @@ def step_schedule(n_iterations: int, halo: int, pressure: bool, smoke: bool) -> 
     return ops
 
 
-def lazy_schedule(n_iterations: int, halo: int, pressure: bool, smoke: bool, margin: int = 16) -> List[tuple]:
+def lazy_schedule(n_iterations: int, halo: int, pressure: bool, smoke: bool, margin: int = 16,
+                  windows: bool = False) -> List[tuple]:
     """The schedule the library runs for linked slabs (csrc/sayal_api.cu step_impl), as data.
 
     Ghost rows are exact to depth D beyond the owned rows.  An SOR iteration costs two rows of depth; an exchange
@@ -73,7 +74,11 @@ def lazy_schedule(n_iterations: int, halo: int, pressure: bool, smoke: bool, mar
       * before the velocity advection when D < margin + 1 (it runs on the owned rows and ONE ghost row each side
         — the smoke sampler reads the new velocity one row away — and gathers from up to `margin` rows away),
     and once at the end of the step for u, v and smoke together.  With halo >= 2 n + margin + 1 that is the only
-    exchange of the step."""
+    exchange of the step.
+
+    windows=True: projection ops carry the depth that is exact when the chunk starts, ("projection", k, depth) —
+    iteration m of the chunk then only needs to sweep the owned rows +- (depth - 2 m), the library's shrinking row
+    window (projection_pack.cu): rows beyond it are already wrong and nobody reads them before the next exchange."""
     if halo < margin + 1 or halo < 2:
         raise ValueError("halo must be >= margin + 1")
     ops: List[tuple] = [("forces",)]
@@ -85,7 +90,7 @@ def lazy_schedule(n_iterations: int, halo: int, pressure: bool, smoke: bool, mar
             ops.append(("exchange", F_U | F_V))
             depth = halo
         k = min(n_iterations - done, depth // 2)
-        ops.append(("projection", k))
+        ops.append(("projection", k, depth) if windows else ("projection", k))
         depth -= 2 * k
         done += k
     if pressure:

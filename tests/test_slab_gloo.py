@@ -39,12 +39,19 @@ class NumpySlab:
         if kind == "forces":
             self.f["v"] += (0.01 * g).astype(np.float32)
         elif kind == "projection":
-            for _ in range(op[1]):
+            own0 = self.row0 - self.lo
+            for m in range(op[1]):
+                # ("projection", k, depth): sweep only the rows that are still exact before iteration m of the chunk
+                # (owned +- (depth - 2 m)); the others keep stale values, like rows outside the library's row window
+                first, last = 0, len(self.f["u"])
+                if len(op) > 2:
+                    first = max(own0 - (op[2] - 2 * m), 0)
+                    last = min(own0 + self.rows + (op[2] - 2 * m), last)
                 for colour in (0, 1):
                     for name in ("u", "v"):
                         a = self.f[name]
                         new = a.copy()
-                        for lr in range(len(a)):
+                        for lr in range(first, last):
                             r = self.lo + lr
                             if r == 0 or r == H - 1 or (r + colour) % 2:
                                 continue
@@ -168,6 +175,39 @@ def test_lazy_schedule_matches_single_domain(world, halo):
     for s in slabs:
         for name in ("u", "v", "smoke"):
             assert np.array_equal(s.owned(name), want[name][s.row0:s.row0 + s.rows]), (name, s.row0)
+
+
+@pytest.mark.parametrize("world,halo", [(2, 6), (3, 9), (2, 18), (3, 18), (4, 5)])
+def test_shrinking_row_window_matches_single_domain(world, halo):
+    """The library's linked slabs sweep, in iteration m of a projection chunk, only the owned rows +- (depth - 2 m):
+    ghost rows beyond that are already wrong.  Same owned rows as the single domain, bit for bit."""
+    full = initial()
+    slabs = []
+    for r in range(world):
+        row0, rows = S.slab_rows(H, world, r)
+        slabs.append(NumpySlab(full, row0, rows, halo, r == 0, r == world - 1))
+    ops = S.lazy_schedule(N_ITER, halo, False, True, margin=REACH, windows=True)
+    assert all(len(op) == 3 and op[2] >= 2 * op[1] for op in ops if op[0] == "projection")
+    for _ in range(3):
+        S.run_schedule_local(slabs, ops)
+    want = single_domain(3)
+    for s in slabs:
+        for name in ("u", "v", "smoke"):
+            assert np.array_equal(s.owned(name), want[name][s.row0:s.row0 + s.rows]), (name, s.row0)
+
+
+def test_too_narrow_window_is_detected():
+    """Sanity of the stand-in: a window that shrinks into rows the owned ones still depend on must change the result."""
+    full = initial()
+    slabs = []
+    for r in range(2):
+        row0, rows = S.slab_rows(H, 2, r)
+        slabs.append(NumpySlab(full, row0, rows, 18, r == 0, r == 1))
+    ops = [(op[0], op[1], op[2] - 2 * op[1] - 1) if op[0] == "projection" else op
+           for op in S.lazy_schedule(N_ITER, 18, False, True, margin=REACH, windows=True)]
+    S.run_schedule_local(slabs, ops)
+    want = single_domain(1)
+    assert any(not np.array_equal(s.owned(n), want[n][s.row0:s.row0 + s.rows]) for s in slabs for n in ("u", "v"))
 
 
 def test_lazy_schedule_shape():
