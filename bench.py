@@ -119,11 +119,12 @@ def dist_env():
     return rank, world, local
 
 
-def workload_config(n_gpus: int):
+def workload_config(n_gpus: int, defaults=None):
+    """defaults: see baseline_config — the reference arm builds its configuration without the product library."""
     from opensayal_b200.synthetic import baseline_config
-    cfg = baseline_config(1)
+    cfg = baseline_config(1, defaults=defaults)
     if n_gpus > 1:  # the same slab per GPU, stacked in y
-        cfg = baseline_config(1, width=1920, height=1080 * n_gpus)
+        cfg = baseline_config(1, width=1920, height=1080 * n_gpus, defaults=defaults)
         cfg["sim.wind_tunnel.pipe_height"] = 270 * n_gpus
         cfg["sim.obstacle.radius"] = 36.0
     return cfg
@@ -176,13 +177,18 @@ def bench_ours_single(args):
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     launches0 = sim.launch_count
     with ClockSampler(0, period=0.004) as clocks:  # several samples inside a region of a few milliseconds
-        sim.stream_delay(min(200000, 2000 + 400 * args.steps))  # the host enqueues the region ahead of the device
-        for k in range(args.steps):
-            flush_l2()
-            starts[k].record(stream)
-            sim.run(1)
-            stops[k].record(stream)
-        sim.sync()
+        done = 0
+        while done < args.steps:  # the host enqueues a chunk behind the gate, then lets the device run it from its queue
+            chunk = min(40, args.steps - done)
+            sim.stream_hold()
+            for k in range(done, done + chunk):
+                flush_l2()
+                starts[k].record(stream)
+                sim.run(1)
+                stops[k].record(stream)
+            sim.stream_release()
+            sim.sync()
+            done += chunk
     launches = sim.launch_count - launches0
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
     ms_per_step = sum(step_ms) / len(step_ms)
@@ -216,70 +222,99 @@ def bench_ours_single(args):
     achieved = alg_bytes_launch / (launch_ms * 1e-3) / 1e9
     peak, peak_src = measured_hbm_peak()
     b_alg = algorithmic_bytes_per_cell_step(n, int(bool(c.enable_pressure)), int(bool(c.enable_smoke and c.wt_smoke != 0)))
-    # physical DRAM bytes per launch of that kernel, from the committed ncu --set full capture of the same plan
-    traffic, traffic_src = None, None
+    # physical DRAM bytes per launch of that kernel, from the committed ncu --set full capture (profiles/traffic.json,
+    # written by tools/ncu_traffic.py); says whether the captured plan is the plan that just ran
+    plan = {"temporal_block": sim.get_option("plan_temporal_block"), "tile_rows_per_warp": sim.get_option("plan_rows_per_warp"),
+            "projection_kernel": sim.get_option("projection_kernel")}
+    traffic, traffic_src, traffic_match, dram_frac = None, None, None, None
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
         try:
             t = json.loads(tp.read_text())
-            # captured for one plan; at this grid any plan's DRAM traffic is the compulsory read of u, v and flags
-            # (18.6 MB) after the L2 flush — the halos that overlapping tiles re-read hit L2
             if t.get("grid", [1920, 1080]) == [W, H]:
                 traffic = t["dram_bytes_per_launch"]
+                traffic_match = (t.get("temporal_block") == plan["temporal_block"]
+                                 and t.get("rows_per_warp") == plan["tile_rows_per_warp"])
                 traffic_src = (f"profiles/traffic.json: {t['source']}; captured with T={t['temporal_block']} "
                                f"rows/warp={t['rows_per_warp']}")
+                # the physical figure beside the algorithmic one: ncu DRAM bytes / this run's launch time / peak
+                dram_frac = round(traffic / (launch_ms * 1e-3) / 1e9 / peak, 4)
         except Exception:
             pass
     roofline = {"bound": "hbm", "kernel": "projection_pack_kernel", "achieved": round(achieved, 1), "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                "traffic_plan_matches": traffic_match, "dram_frac": dram_frac,
                 "peak_source": peak_src, "launches_per_step": passes, "ms_per_launch": round(launch_ms, 5),
                 "algorithmic_bytes_per_launch": alg_bytes_launch,
                 "share_of_step": round(proj_ms / ms_per_step, 3),
                 "whole_step": {"algorithmic_bytes_per_cell_step": b_alg,
                                "achieved_GBps": round(value * b_alg / 1e9, 1),
                                "frac": round(value * b_alg / 1e9 / peak, 4)},
-                "note": "algorithmic bytes give no credit for temporal blocking (T iterations per HBM pass), so "
-                        "frac > 1 means fewer physical bytes than one pass per sweep; see DESIGN.md"}
+                "note": "algorithmic bytes give no credit for temporal blocking (T iterations per HBM pass) or L2 "
+                        "residency, so frac > 1 means fewer physical bytes than one pass per sweep; dram_frac is the "
+                        "physical DRAM traffic of the same launch against the same peak; see DESIGN.md"}
 
-    # ---- end to end from pinned host buffers through the public API
+    # ---- end to end from pinned host buffers through the public API: one batched upload, K steps with a host-side
+    # Source each (main.cu:97), one batched download — wall clock, copies inside the timed region
     pinned = {k: torch.empty((H, W), dtype=torch.float32).pin_memory() for k in ("u", "v", "smoke")}
     for k, a in (("u", u), ("v", v), ("smoke", sm)):
         pinned[k].numpy()[...] = a
     out = {k: torch.empty((H, W), dtype=torch.float32).pin_memory() for k in ("u", "v", "smoke")}
-    import ctypes as C
-    from opensayal_b200 import _abi
-    lib = _abi.load()
     src = Source()  # inactive, passed from the host every step like main.cu:97 does
+    field_bytes = 3 * cells * 4
+
+    def e2e_once():
+        sim.sync()
+        t0 = time.perf_counter()
+        sim.set_fields_from({k: t_.data_ptr() for k, t_ in pinned.items()})
+        for _ in range(args.steps):
+            sim.step_async(src, c.d_t)
+        sim.get_fields_into({k: t_.data_ptr() for k, t_ in out.items()})
+        return time.perf_counter() - t0
+
+    e2e_once()  # untimed: first touch of the pinned pages by the copy engine
+    e2e_s = min(e2e_once() for _ in range(3))
+    assert np.isfinite(out["u"].numpy()).all()
+    # the copies alone (same calls, no steps): what the PCIe link of this box gives for these buffers
     sim.sync()
     t0 = time.perf_counter()
-    for k in ("u", "v", "smoke"):
-        _abi.check(lib.sayal_set_field(sim._sim, _abi.FIELD_NAMES[k], C.c_void_p(pinned[k].data_ptr())))
-    for _ in range(args.steps):
-        sim.step_async(src, c.d_t)
-    for k in ("u", "v", "smoke"):
-        _abi.check(lib.sayal_get_field(sim._sim, _abi.FIELD_NAMES[k], C.c_void_p(out[k].data_ptr())))
+    sim.set_fields_from({k: t_.data_ptr() for k, t_ in pinned.items()})
+    sim.sync()
     t1 = time.perf_counter()
-    assert np.isfinite(out["u"].numpy()).all()
-    e2e_value = cells * args.steps / (t1 - t0)
-    field_bytes = 3 * cells * 4
+    sim.get_fields_into({k: t_.data_ptr() for k, t_ in out.items()})
+    t2 = time.perf_counter()
+    e2e_value = cells * args.steps / e2e_s
     e2e = {"value": e2e_value, "unit": "cell-steps/s", "h2d_bytes_per_step": field_bytes / args.steps + 20,
-           "d2h_bytes_per_step": field_bytes / args.steps,
-           "protocol": "set_field(u,v,smoke) from pinned host + K x sayal_step(host Source) + get_field(u,v,smoke), wall clock"}
+           "d2h_bytes_per_step": field_bytes / args.steps, "seconds": e2e_s,
+           "h2d_GBps": round(field_bytes / (t1 - t0) / 1e9, 2), "d2h_GBps": round(field_bytes / (t2 - t1) / 1e9, 2),
+           "protocol": "sayal_set_fields(u,v,smoke) from pinned host + K x sayal_step(host Source) + sayal_get_fields(u,v,smoke), "
+                       "wall clock, best of 3"}
+
+    strong = None
+    if not os.environ.get("SAYAL_BENCH_SKIP_STRONG"):
+        plan_text = sim.plan_log()
+        sim.close()
+        del flush
+        torch.cuda.empty_cache()
+        from opensayal_b200.slab import strong_16384_record
+        strong = strong_16384_record(1, 0, 0)
+    else:
+        plan_text = sim.plan_log()
+        sim.close()
 
     cpu = None if args.skip_cpu_baseline else cpu_baseline_port(cfg, threads=1, target_seconds=12.0)
     line = {
         "metric": "cell-steps/sec (n=50 SOR)", "value": value, "unit": "cell-steps/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_block(cfg, 1, {"temporal_block": sim.get_option("plan_temporal_block"),
-                                        "tile_rows_per_warp": sim.get_option("plan_rows_per_warp"),
-                                        "projection_kernel": sim.get_option("projection_kernel")}),
+        "config": config_block(cfg, 1),
+        "plan": dict(plan, candidates=plan_text.strip().split("\n")),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
         "clocks": clocks.summary(),
         "steady_state_ms_per_step_l2_warm": warm_ms,
         "stage_ms": {"projection": proj_ms},
+        "strong_16384": strong,
     }
-    sim.close()
     return line
 
 
@@ -315,7 +350,10 @@ def bench_reference(args):
     from oracle.oracle import REF_LIB, RefSim
     from opensayal_b200.synthetic import synthetic_fields
 
-    cfg = workload_config(1)  # the reference is single-GPU (no multi-GPU code exists in it)
+    from oracle.oracle import reference_defaults
+    # the reference is single-GPU (no multi-GPU code exists in it); its configuration is built without the product
+    # library (reference_defaults), so this arm maps oracle/_ref only
+    cfg = workload_config(1, defaults=reference_defaults)
     c = cfg.c
     cells = c.width * c.height
     warm = max(args.warmup, 3)
@@ -336,13 +374,31 @@ def bench_reference(args):
         ms_per_step = sum(ms) / len(ms)
         value = cells / (ms_per_step * 1e-3)
         launches = 1 + 2 * c.proj_n + 1 + 2 + 3  # forces, 2n sweeps, extrapolation, 2 + 3 advection
+        ref.close()
+        # the same with the reference's shipped default fluid.viscosity = 0.001 (config_parser.cpp:117): n more
+        # (racy) diffusion launches per step, fluid.cu:775-777 — reported beside the headline, not instead of it
+        cfg_v = workload_config(1, defaults=reference_defaults)
+        cfg_v["fluid.viscosity"] = 0.001
+        ref = RefSim(cfg_v.c, device=0)
+        for name, a in (("u", u), ("v", v), ("smoke", sm)):
+            ref.set_field(name, a)
+        ref.run_timed(warm)
+        ms_v = []
+        for _ in range(args.steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            ms_v.append(ref.run_timed(1))
+        ms_visc = sum(ms_v) / len(ms_v)
         line = {
             "impl": "reference", "metric": "cell-steps/sec (n=50 SOR)", "value": value, "unit": "cell-steps/s",
             "n_gpus": 1, "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_block(cfg, 1, {"reference_build": "oracle/_ref: /root/reference/src/fluid.cu + helper.cu unmodified, "
-                                            "-O3 --use_fast_math -rdc=true -gencode arch=compute_100,code=sm_100, block (64,1), "
-                                            "fluid.viscosity=0 (H1)"}),
+            "config": config_block(cfg, 1),
+            "reference_build": "oracle/_ref: /root/reference/src/fluid.cu + helper.cu unmodified, -O3 --use_fast_math "
+                               "-rdc=true -gencode arch=compute_100,code=sm_100, block (64,1), fluid.viscosity=0 (H1)",
+            "default_viscosity_0.001": {"ms_per_step": ms_visc, "value": cells / (ms_visc * 1e-3),
+                                        "note": "same workload with the reference's shipped default fluid.viscosity "
+                                                "(config_parser.cpp:117): + n diffusion launches per step"},
             "cpu_baseline": {"value": value, "unit": "cell-steps/s", "cores": 0, "kind": "reference",
                              "sample": f"{args.steps} full steps; OpenSayal has no CPU path, its implementation of the "
                                        "step is CUDA and ran on the same B200 (0 host cores on the data path)"},
@@ -358,7 +414,7 @@ def bench_reference(args):
     return {"impl": "reference", "metric": "cell-steps/sec (n=50 SOR)", "value": cpu["value"], "unit": "cell-steps/s",
             "n_gpus": 1, "steps": args.steps, "warmup": warm, "ms_per_step": cells / cpu["value"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_block(cfg, 1, {"note": "oracle/_ref unavailable: CPU port on all host threads"}),
+            "config": config_block(cfg, 1), "note": "oracle/_ref unavailable: CPU port on all host threads",
             "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SAYAL_ABI_VERSION 2
+#define SAYAL_ABI_VERSION 3
 
 /* error codes */
 #define SAYAL_OK 0
@@ -33,6 +33,7 @@ extern "C" {
 #define SAYAL_EPARSE (-4)   /* config file is not valid JSON / wrong value type */
 #define SAYAL_ENOMEM (-5)
 #define SAYAL_EBUSY (-6)    /* frame ring full: acquire a frame first */
+#define SAYAL_ELINK (-7)    /* a neighbouring slab did not answer (or runs another plan): fields are not valid */
 
 /* fields, for sayal_get_field / sayal_set_field / sayal_device_ptr */
 enum sayal_field {
@@ -139,13 +140,26 @@ int sayal_sync(sayal_sim* sim);
  * For a slab sim the buffer holds the owned rows only (rows*W elements). Synchronous. */
 int sayal_get_field(sayal_sim* sim, int32_t field, void* host_dst);
 int sayal_set_field(sayal_sim* sim, int32_t field, const void* host_src);
+/* The same for `n` fields at once (what main.cu would do around a batch of updates): the copies are enqueued on the
+ * sim's stream back to back.  sayal_get_fields waits once, after the last copy.  sayal_set_fields does not wait at
+ * all when the sources are pinned host memory — the caller keeps them untouched until the next synchronous call
+ * (sayal_sync, sayal_get_field(s), ...); pageable sources are staged by the runtime before the call returns. */
+int sayal_get_fields(sayal_sim* sim, int32_t n, const int32_t* fields, void* const* host_dsts);
+int sayal_set_fields(sayal_sim* sim, int32_t n, const int32_t* fields, const void* const* host_srcs);
+/* Device-to-device forms for a caller that already lives on the GPU (a renderer, an interop tensor): `dev_*` holds
+ * the owned rows in the reference layout (row pitch W elements) on the sim's device.  Ordered on the sim's stream,
+ * asynchronous: the caller orders its own streams against sayal_stream() / sayal_sync(). */
+int sayal_get_field_device(sayal_sim* sim, int32_t field, void* dev_dst);
+int sayal_set_field_device(sayal_sim* sim, int32_t field, const void* dev_src);
 /* Zero-copy view for a renderer (replaces dereferencing Fluid::d_* on device,
  * graphics_handler.cu:269-283): device pointer to memory row 0 of the local array, its pitch in
  * elements, the first global memory row it holds and the number of rows held (incl. ghost rows). */
 int sayal_device_ptr(sayal_sim* sim, int32_t field, void** dev_ptr, int64_t* pitch_elems,
                      int32_t* first_row, int32_t* n_rows);
 /* Fluid::min_pressure / max_pressure (fluid.cuh:61-62, fluid.cu:778-787), of the last step.
- * Synchronises the stream. Only meaningful when enable_pressure. */
+ * Synchronises the stream. Only meaningful when enable_pressure.  Linked slabs return the range of the WHOLE
+ * domain (reduced along the chain of slabs inside the step), the one pair the reference's frame is coloured with
+ * (graphics_handler.cu:288-289); sayal_render_pixels / sayal_frame_submit use the same pair. */
 int sayal_pressure_range(sayal_sim* sim, float* min_p, float* max_p);
 /* Fluid::get_general_velocity(x, y) (fluid.cu:541-545) at `n` host-supplied points. */
 int sayal_sample_velocity(sayal_sim* sim, int32_t n, const float* xs, const float* ys, float* out_u,
@@ -232,24 +246,35 @@ int sayal_path_lines(sayal_sim* sim, const sayal_visual* v, float d_t, int32_t* 
  * blocked), "temporal_block" (iterations per pass, 0 = choose), "tile_rows_per_warp" (0 = choose, 8/10/12),
  * "autotune" (time candidate tile plans on first use), "use_graph", "use_pdl", "fuse_forces" / "fuse_extrapolation"
  * (fold those stages into the first / last projection pass), "order_tiles" (issue expensive tiles first),
- * "advect_kernel", "advect_margin", "overlap_exchange"; "debug_timeline" / "debug_skip" are profiling aids (the
- * latter leaves stages out and does change results).  get: the same plus "plan_temporal_block",
- * "plan_rows_per_warp", "halo_overflow", "link_error", "pitch", "local_rows", "own_lo", "own_hi".  No other option
- * changes results. */
+ * "advect_kernel", "advect_margin", "overlap_exchange", "slab_push" (linked slabs: passes push their own edge rows);
+ * "debug_timeline" / "debug_skip" are profiling aids (the latter leaves stages out and does change results).  get:
+ * the same plus "plan_temporal_block", "plan_rows_per_warp", "push_mode", "halo_overflow", "link_error", "pitch",
+ * "local_rows", "own_lo", "own_hi".  No other option changes results. */
 int sayal_set_option(sayal_sim* sim, const char* key, int64_t value);
 int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value);
+/* The candidates the tile-plan tuner timed for the last projection it planned, as text (one "rows T model ms" line
+ * each, the chosen one marked): copies at most `capacity` bytes incl. the terminator; returns the full length. */
+int sayal_plan_log(sayal_sim* sim, char* buf, int32_t capacity);
 /* Profiling only (option "debug_timeline" = 1): per-CTA timestamps of the last projection pass, 5 int64 per tile
  * {entry, tile loaded, sweeps done, stores issued (globaltimer ns), SM id}. */
 int sayal_debug_timeline(sayal_sim* sim, int64_t* host_dst, int32_t max_tiles, int32_t* n_tiles);
 /* Measurement aid: hold the sim's stream for `microseconds` (<= 1e6) with a one-thread spin kernel, so that a whole
  * timed region can be enqueued before the device starts on it (host launch jitter then cannot drain the queue). */
 int sayal_stream_delay(sayal_sim* sim, int64_t microseconds);
+/* The same with the host deciding when: sayal_stream_hold enqueues a one-thread kernel that spins on a word of
+ * mapped host memory; whatever is enqueued behind it starts when sayal_stream_release is called (or after 20 s).
+ * Multi-GPU runs enqueue their whole region on every rank, meet at a host barrier and release together. */
+int sayal_stream_hold(sayal_sim* sim);
+int sayal_stream_release(sayal_sim* sim);
 /* Host-only introspection (no CUDA call, no sim): the passes the tiled projection takes for `iterations` iterations
  * with temporal block T on an array of `pitch` x `local_rows` cells whose rows [own_lo, own_hi) are owned; ghost_depth
  * < 0: every pass sweeps all rows, else pass k sweeps the owned rows +- (ghost_depth - 2 * iterations done before it).
- * Per pass 11 int32: iterations, row_lo, row_hi, halo_x, halo_y, stride_x, stride_y, tiles_x, tiles_y, tile_w, tile_h.
+ * ghost_depth <= -2: push mode with halo = -ghost_depth (pass k sweeps the owned rows +- 2 x its iterations on every
+ * side where the array holds ghost rows, and writes the owned rows only).
+ * Per pass 15 int32: iterations, row_lo, row_hi, halo_x, halo_y, stride_x, stride_y, tiles_x, tiles_y, tile_w, tile_h,
+ * write_lo, write_hi, pushing tiles towards side 0, towards side 1.
  * Tile (a, b) covers columns [a stride_x, +tile_w) and rows [row_lo + b stride_y, +tile_h) and writes the part that
- * is at least a halo away from every edge that has a neighbouring tile. */
+ * is at least a halo away from every edge that has a neighbouring tile, clipped to [write_lo, write_hi). */
 int sayal_debug_pass_plans(int32_t pitch, int32_t local_rows, int32_t own_lo, int32_t own_hi, int32_t rows_per_warp,
                            int32_t temporal_block, int32_t iterations, int32_t ghost_depth, int32_t* out,
                            int32_t capacity, int32_t* n_passes);
@@ -266,18 +291,27 @@ int sayal_slab_pack_edge(sayal_sim* sim, int32_t side, int32_t nrows, int32_t fi
 int sayal_slab_unpack_ghost(sayal_sim* sim, int32_t side, int32_t nrows, int32_t field_mask,
                             const void* dev_buf);
 
-/* ---- slab links: ghost rows over NVLink peer memory, no host in the loop (slab_exchange.cu) ----------------
- * Each slab sim owns one neighbour-writable device block.  Processes trade its CUDA IPC handle once
- * (export on the owner, connect on the neighbour; `side` 0 = the neighbour holding the rows above mine in memory,
- * 1 = below); slabs living in one process connect directly.  Once a slab has a neighbour, sayal_step / sayal_run
- * run the whole slab schedule on the sim's stream, graph-captured by sayal_run: ghost rows lose two rows of
- * validity per SOR iteration and are refreshed (u, v) only when the next operation needs more depth than is left,
- * and once at the end of the step (u, v to the full halo, smoke advect_margin + 2 rows) under the interior smoke
- * advection.  With halo >= 2 n + advect_margin + 2 a step has exactly one exchange.  The ranks must issue the same
- * sequence of steps and use the same halo and advect_margin. */
-#define SAYAL_IPC_HANDLE_BYTES 64
-int sayal_slab_ipc_export(sayal_sim* sim, void* handle_out /* 64 bytes */, int64_t* stage_elems);
-int sayal_slab_ipc_connect(sayal_sim* sim, int32_t side, const void* handle /* 64 bytes */, int64_t stage_elems);
+/* ---- slab links: ghost rows over NVLink peer memory, no host in the loop (slab_exchange.cu, projection_pack.cu) ---
+ * Each slab sim owns one neighbour-writable device block (control words + receive areas) and keeps u, v and their
+ * back buffers in one allocation.  Processes trade one opaque blob once (export on the owner, connect on the
+ * neighbour; `side` 0 = the neighbour holding the rows above mine in memory, 1 = below) — it carries the CUDA IPC
+ * handles of both allocations and the slab's geometry; slabs living in one process connect directly.  Link before
+ * the first step.  Once a slab has a neighbour, sayal_step / sayal_run run the whole slab schedule on the sim's
+ * stream, graph-captured by sayal_run:
+ *   push mode (default; option "slab_push"): every projection pass sweeps the owned rows plus 2 x its iterations of
+ *     ghost rows, and the tiles that produce the slab's edge rows store them a second time straight into the
+ *     neighbour's ghost rows and publish a flag the neighbour's next pass waits on — compute and exchange are one
+ *     kernel, a step needs halo >= max(2 T, advect_margin + 2) ghost rows (T = iterations per pass, at most 8);
+ *   otherwise: ghost rows lose two rows of validity per SOR iteration and are refreshed by an exchange kernel only
+ *     when the next operation needs more depth than is left (halo >= 2 n + advect_margin + 2: never inside a step).
+ * Either way one exchange at the end of the step carries u, v (halo rows) and smoke (advect_margin + 2 rows), hidden
+ * under the interior smoke advection.  The ranks must issue the same sequence of steps and use the same halo,
+ * advect_margin and temporal_block.  A neighbour that does not answer within 2 s, or that splits the projection
+ * into different passes, raises a sticky error: the next sayal_sync / sayal_run / sayal_get_field(s) returns
+ * SAYAL_ELINK and the fields are not valid. */
+#define SAYAL_LINK_INFO_BYTES 256
+int sayal_slab_ipc_export(sayal_sim* sim, void* info_out /* SAYAL_LINK_INFO_BYTES */);
+int sayal_slab_ipc_connect(sayal_sim* sim, int32_t side, const void* info /* SAYAL_LINK_INFO_BYTES */);
 int sayal_slab_connect_local(sayal_sim* sim, int32_t side, sayal_sim* neighbour);
 /* One exchange of the edge rows of the fields in field_mask (1 = U, 2 = V: `halo` rows; 4 = SMOKE: advect_margin + 2
  * rows) with both neighbours. */

@@ -13,7 +13,8 @@ PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "libsayal_b200.so"
 
 SAYAL_OK = 0
-SAYAL_EINVAL, SAYAL_ECUDA, SAYAL_EIO, SAYAL_EPARSE, SAYAL_ENOMEM = -1, -2, -3, -4, -5
+SAYAL_EINVAL, SAYAL_ECUDA, SAYAL_EIO, SAYAL_EPARSE, SAYAL_ENOMEM, SAYAL_EBUSY, SAYAL_ELINK = -1, -2, -3, -4, -5, -6, -7
+LINK_INFO_BYTES = 256
 U, V, P, SMOKE, IS_SOLID, TOTAL_S = range(6)
 FIELD_NAMES = {"u": U, "v": V, "p": P, "smoke": SMOKE, "is_solid": IS_SOLID, "total_s": TOTAL_S}
 
@@ -137,6 +138,10 @@ SYMBOLS = [
     ("sayal_sync", C.c_int, [_simp]),
     ("sayal_get_field", C.c_int, [_simp, C.c_int32, C.c_void_p]),
     ("sayal_set_field", C.c_int, [_simp, C.c_int32, C.c_void_p]),
+    ("sayal_get_field_device", C.c_int, [_simp, C.c_int32, C.c_void_p]),
+    ("sayal_set_field_device", C.c_int, [_simp, C.c_int32, C.c_void_p]),
+    ("sayal_get_fields", C.c_int, [_simp, C.c_int32, _i32p, C.POINTER(C.c_void_p)]),
+    ("sayal_set_fields", C.c_int, [_simp, C.c_int32, _i32p, C.POINTER(C.c_void_p)]),
     ("sayal_device_ptr", C.c_int, [_simp, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("sayal_pressure_range", C.c_int, [_simp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
@@ -151,20 +156,23 @@ SYMBOLS = [
     ("sayal_get_option", C.c_int, [_simp, C.c_char_p, C.POINTER(C.c_int64)]),
     ("sayal_debug_timeline", C.c_int, [_simp, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     ("sayal_stream_delay", C.c_int, [_simp, C.c_int64]),
+    ("sayal_stream_hold", C.c_int, [_simp]),
+    ("sayal_stream_release", C.c_int, [_simp]),
+    ("sayal_plan_log", C.c_int, [_simp, C.c_char_p, C.c_int32]),
     ("sayal_debug_pass_plans", C.c_int, [C.c_int32] * 8 + [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
     ("sayal_launch_count", C.c_int64, [_simp]),
     ("sayal_stream", C.c_void_p, [_simp]),
     ("sayal_slab_pack_edge", C.c_int, [_simp, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     ("sayal_slab_unpack_ghost", C.c_int, [_simp, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
-    ("sayal_slab_ipc_export", C.c_int, [_simp, C.c_void_p, C.POINTER(C.c_int64)]),
-    ("sayal_slab_ipc_connect", C.c_int, [_simp, C.c_int32, C.c_void_p, C.c_int64]),
+    ("sayal_slab_ipc_export", C.c_int, [_simp, C.c_void_p]),
+    ("sayal_slab_ipc_connect", C.c_int, [_simp, C.c_int32, C.c_void_p]),
     ("sayal_slab_connect_local", C.c_int, [_simp, C.c_int32, _simp]),
     ("sayal_slab_exchange", C.c_int, [_simp, C.c_int32]),
     ("sayal_last_error", C.c_char_p, []),
     ("sayal_abi_version", C.c_int, []),
 ]
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 

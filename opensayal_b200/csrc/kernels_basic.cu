@@ -263,7 +263,9 @@ __global__ void pressure_range_kernel(Grid g, const float* __restrict__ p, int32
 int launch_pressure_range(Sim* s) {
   range_init_kernel<<<1, 1, 0, s->stream>>>(s->d_range);
   SAYAL_LAUNCH_CHECK(s, "range_init_kernel");
-  pressure_range_kernel<<<148 * 4, 256, 0, s->stream>>>(s->g, s->p, s->d_range);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+  pressure_range_kernel<<<sms * 4, 256, 0, s->stream>>>(s->g, s->p, s->d_range);
   SAYAL_LAUNCH_CHECK(s, "pressure_range_kernel");
   return SAYAL_OK;
 }

@@ -129,6 +129,29 @@ __device__ __forceinline__ Mult lut_load(const LutEntry* lut, unsigned byte_offs
   return m;
 }
 
+// In-pass push of a linked y-slab (no reference equivalent: OpenSayal is single-GPU).  A pass of `it`
+// iterations needs 2 it exact ghost rows and leaves none; instead of carrying 2 n + margin ghost rows through the
+// whole step (recomputed by every slab), the tiles that produce the slab's edge rows store them a second time —
+// straight into the neighbour's ghost rows of ITS output arrays, over NVLink — and the last of them publishes a pass
+// flag.  The neighbour's next pass waits for that flag only in the warps that load ghost rows.  Ping-pong makes
+// the protocol acknowledgement-free: pass k of the neighbour reads the buffer I will write in pass k + 1, and I
+// can only start pass k + 1 after its pass-k flag, which it publishes after those reads.
+struct PushArgs {
+  int on;                    // bit d: a neighbour on side d (0 = low memory rows) takes this pass's edge rows
+  int pass_index;            // 0: the ghost rows came with the end-of-step exchange (stream order), nothing to wait for
+  int signature;             // (iterations << 8) | passes of the step's plan: both sides must agree
+  int src_lo[2], src_hi[2];  // my local rows that travel to side d
+  int dst_row0[2];           // row of src_lo[d] in the neighbour's arrays
+  int n_pushers[2];          // tiles whose written rows meet [src_lo, src_hi): the last one publishes the flag
+  float* peer_u[2];          // the neighbour's output arrays of this pass
+  float* peer_v[2];
+  unsigned* peer_words[2];   // control words of the neighbours / mine (sayal_internal.h)
+  const unsigned* my_words;
+  unsigned* ticket;          // [2]
+  const unsigned* step_seq;
+  int* link_error;
+};
+
 struct PackArgs {
   Grid g;
   const float* __restrict__ u_in;
@@ -155,6 +178,9 @@ struct PackArgs {
   // like rows outside the array (not loaded, never written); the window's outer edge behaves like a tile edge
   // without a neighbour, which is what costs the next two rows per iteration.
   int row_lo, row_hi;
+  int write_lo, write_hi;  // rows this pass may write: the window, or (push mode) the owned rows only — the ghost
+                           // rows of the output arrays belong to the neighbours' pushes
+  PushArgs push;
   int tiles_x;           // tiles per tile row (the grid is one-dimensional: blockIdx.x -> order -> tile)
   const int* order;      // tiles sorted by cost, most expensive first (tile_order_kernel), or null for row-major
   int extrap_on;  // the step's last pass: apply_extrapolation_at (fluid.cu:720-733) on the tile before it is stored
@@ -346,6 +372,28 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   unsigned fl[RY];
   u64 vlast02, vlast13;
 
+  // rows this tile will write (everything >= halo away from an edge that has a neighbouring tile, clipped to the
+  // write window), and — linked slabs in push mode — whether they include edge rows a neighbour is waiting for
+  const int vy0 = max(Y0 == a.row_lo ? a.row_lo : Y0 + a.halo_y, a.write_lo);
+  const int vy1 = min(Y0 + TH >= a.row_hi ? a.row_hi : Y0 + TH - a.halo_y, a.write_hi);
+  const bool push0 = (a.push.on & 1) && vy0 < a.push.src_hi[0] && vy1 > a.push.src_lo[0];
+  const bool push1 = (a.push.on & 2) && vy0 < a.push.src_hi[1] && vy1 > a.push.src_lo[1];
+  if (a.push.on && a.push.pass_index > 0) {
+    // The neighbour's previous pass stored its edge rows into my ghost rows: the warps that load such rows (and
+    // warp 0 of a tile that pushes, which must not overwrite rows the neighbour may still be reading) wait for its
+    // flag; every other warp goes straight to its loads and the wait hides behind them.
+    const unsigned target = (*a.push.step_seq << 10) + (unsigned)a.push.pass_index;
+    const bool need0 = (a.push.on & 1) && (lr0 - (w == 0 ? 1 : 0) < a.write_lo || (w == 0 && push0));
+    const bool need1 = (a.push.on & 2) && (lr0 + RY > a.write_hi || (w == 0 && push1));
+    if (need0 || need1) {
+      if (lane == 0) {
+        if (need0) spin_until(a.push.my_words + LW_PFLAG + 0, target, a.push.link_error);
+        if (need1) spin_until(a.push.my_words + LW_PFLAG + 1, target, a.push.link_error);
+      }
+      __syncwarp();
+    }
+  }
+
   const bool col_ok = x < g.pitch;  // pitch is a multiple of 4: a lane's four columns are in or out together
 #pragma unroll
   for (int r = 0; r < RY; r++) {
@@ -354,8 +402,10 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
     unsigned f = 0;
     if (col_ok && lr < a.row_hi) {
       size_t k = (size_t)lr * g.pitch + x;
-      uu = *reinterpret_cast<const float4*>(a.u_in + k);
-      vv = *reinterpret_cast<const float4*>(a.v_in + k);
+      // .cg: read through L2 — ghost rows may have been stored by a neighbouring GPU since this SM last saw them,
+      // and a tile reads every element exactly once anyway
+      uu = __ldcg(reinterpret_cast<const float4*>(a.u_in + k));
+      vv = __ldcg(reinterpret_cast<const float4*>(a.v_in + k));
       f = *reinterpret_cast<const unsigned*>(a.flags + k);
     }
     U02[r] = pk(uu.x, uu.z);
@@ -434,7 +484,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   if (w == 0) {
     float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (col_ok && Y0 - 1 >= a.row_lo && Y0 - 1 < a.row_hi) {
-      vv = *reinterpret_cast<const float4*>(a.v_in + (size_t)(Y0 - 1) * g.pitch + x);
+      vv = __ldcg(reinterpret_cast<const float4*>(a.v_in + (size_t)(Y0 - 1) * g.pitch + x));
       if (FORCES) {
         float4 unused = make_float4(0.f, 0.f, 0.f, 0.f);
         forces_on_load(a, x, Y0 - 1, unused, vv);
@@ -577,21 +627,49 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   // write the part of the tile that is exact: everything >= halo away from an edge that has a neighbour
   const int vx0 = X0 == 0 ? 0 : X0 + a.halo_x;
   const int vx1 = X0 + TW >= g.pitch ? g.pitch : X0 + TW - a.halo_x;
-  const int vy0 = Y0 == a.row_lo ? a.row_lo : Y0 + a.halo_y;
-  const int vy1 = Y0 + TH >= a.row_hi ? a.row_hi : Y0 + TH - a.halo_y;
   if (x >= vx0 && x < vx1) {
 #pragma unroll
     for (int r = 0; r < RY; r++) {
       int lr = lr0 + r;
       if (lr >= vy0 && lr < vy1) {
         size_t k = (size_t)lr * g.pitch + x;
-        *reinterpret_cast<float4*>(a.u_out + k) = make_float4(lo(U02[r]), lo(U13[r]), hi(U02[r]), hi(U13[r]));
+        const float4 uo = make_float4(lo(U02[r]), lo(U13[r]), hi(U02[r]), hi(U13[r]));
+        *reinterpret_cast<float4*>(a.u_out + k) = uo;
         u64 p02 = r < RY - 1 ? V02[r < RY - 1 ? r : 0] : vlast02;
         u64 p13 = r < RY - 1 ? V13[r < RY - 1 ? r : 0] : vlast13;
-        *reinterpret_cast<float4*>(a.v_out + k) = make_float4(lo(p02), lo(p13), hi(p02), hi(p13));
+        const float4 vo = make_float4(lo(p02), lo(p13), hi(p02), hi(p13));
+        *reinterpret_cast<float4*>(a.v_out + k) = vo;
         if (PRESSURE) {
           u64 q02 = lds64(sp_warp + r * 128), q13 = lds64(sp_warp + r * 128 + 64);
           *reinterpret_cast<float4*>(a.p + k) = make_float4(lo(q02), lo(q13), hi(q02), hi(q13));
+        }
+        if (push0 && lr >= a.push.src_lo[0] && lr < a.push.src_hi[0]) {  // my edge rows = the neighbour's ghost rows
+          size_t kp = (size_t)(lr - a.push.src_lo[0] + a.push.dst_row0[0]) * g.pitch + x;
+          *reinterpret_cast<float4*>(a.push.peer_u[0] + kp) = uo;
+          *reinterpret_cast<float4*>(a.push.peer_v[0] + kp) = vo;
+        }
+        if (push1 && lr >= a.push.src_lo[1] && lr < a.push.src_hi[1]) {
+          size_t kp = (size_t)(lr - a.push.src_lo[1] + a.push.dst_row0[1]) * g.pitch + x;
+          *reinterpret_cast<float4*>(a.push.peer_u[1] + kp) = uo;
+          *reinterpret_cast<float4*>(a.push.peer_v[1] + kp) = vo;
+        }
+      }
+    }
+  }
+  if (push0 || push1) {  // uniform over the CTA
+    __syncthreads();     // every thread's stores are issued before thread 0 fences at system scope
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      const unsigned published = (*a.push.step_seq << 10) + (unsigned)a.push.pass_index + 1u;
+#pragma unroll
+      for (int d = 0; d < 2; d++) {
+        if (!(d == 0 ? push0 : push1)) continue;
+        if (atomicAdd(&a.push.ticket[d], 1u) == (unsigned)a.push.n_pushers[d] - 1u) {  // the side's last tile
+          a.push.ticket[d] = 0;
+          unsigned* w = a.push.peer_words[d];
+          w[LW_PITER + (1 - d)] = (unsigned)a.push.signature;
+          __threadfence_system();
+          st_release_sys(w + LW_PFLAG + (1 - d), published);
         }
       }
     }
@@ -605,8 +683,10 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
 // Cost class of every tile of one geometry: the number of its warps that take the table path (same test as the
 // pack kernel: a row whose flags differ from the warp's middle row, or a middle row next to a horizontal
 // boundary).  One CTA per tile, thread layout as in the pack kernel.
+// edge_first (push mode): the first / last tile row (bit 0 / bit 1) produces the rows a neighbouring GPU waits for
+// and goes to the front of the issue order whatever it costs.
 __global__ void tile_cost_kernel(Grid g, const uint8_t* __restrict__ flags, int ry, int stride_x, int stride_y, int tiles_x,
-                                 int row_lo, int row_hi, int* __restrict__ cost) {
+                                 int tiles_y, int edge_first, int row_lo, int row_hi, int* __restrict__ cost) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int tile = blockIdx.x, tile_y = tile / tiles_x, tile_x = tile - tile_y * tiles_x;
   const int x = tile_x * stride_x + 4 * lane, lr0 = row_lo + tile_y * stride_y + w * ry;
@@ -632,7 +712,8 @@ __global__ void tile_cost_kernel(Grid g, const uint8_t* __restrict__ flags, int 
   __syncthreads();
   if (lane == 0 && irr) atomicAdd(&s_count, 1);
   __syncthreads();
-  if (threadIdx.x == 0) cost[tile] = s_count;
+  const bool edge = ((edge_first & 1) && tile_y == 0) || ((edge_first & 2) && tile_y == tiles_y - 1);
+  if (threadIdx.x == 0) cost[tile] = edge ? 32 : s_count;
 }
 
 // Counting sort of the tiles by cost, most expensive first (one CTA; costs are 0..32; ties in any order).
@@ -721,11 +802,11 @@ int launch_pass(Sim* s, const Variant& v, const PackArgs& a, dim3 grid, cudaStre
 // Device array with the tiles of geometry (variant, iterations-per-pass) in issue order; built on first use
 // (two small kernels on the sim's stream) and cached.  Returns null — row-major order — when the cache is full,
 // the option is off, or the stream is being captured and the geometry has not been seen before.
-const int* tile_order(Sim* s, int variant, int it, const Geometry& q, int row_lo, int row_hi) {
+const int* tile_order(Sim* s, int variant, int it, const Geometry& q, int row_lo, int row_hi, int edge_first = 0) {
   if (!s->order_tiles) return nullptr;
   for (int k = 0; k < s->n_orders; k++)
     if (s->orders[k].variant == variant && s->orders[k].it == it && s->orders[k].row_lo == row_lo &&
-        s->orders[k].row_hi == row_hi)
+        s->orders[k].row_hi == row_hi && s->orders[k].edge_first == edge_first)
       return s->orders[k].order;
   const int tiles = q.tiles_x * q.tiles_y;
   if (s->n_orders == Sim::kMaxOrders || tiles <= 1) return nullptr;
@@ -738,40 +819,103 @@ const int* tile_order(Sim* s, int variant, int it, const Geometry& q, int row_lo
     return nullptr;
   }
   const Variant& v = kVariants[variant];
-  tile_cost_kernel<<<tiles, v.nw * 32, 0, s->stream>>>(s->g, s->flags, v.ry, q.stride_x, q.stride_y, q.tiles_x, row_lo, row_hi,
-                                                      buf + tiles);
+  tile_cost_kernel<<<tiles, v.nw * 32, 0, s->stream>>>(s->g, s->flags, v.ry, q.stride_x, q.stride_y, q.tiles_x, q.tiles_y,
+                                                      edge_first, row_lo, row_hi, buf + tiles);
   tile_order_kernel<<<1, 1024, 0, s->stream>>>(buf + tiles, tiles, buf);
   if (cudaGetLastError() != cudaSuccess) {
     cudaFree(buf);
     return nullptr;
   }
-  s->orders[s->n_orders++] = {variant, it, row_lo, row_hi, buf};
+  s->orders[s->n_orders++] = {variant, it, row_lo, row_hi, edge_first, buf};
   return buf;
 }
 
-int run_passes(Sim* s, int variant, int T, int iterations, float d_t, bool with_forces = false, bool with_extrap = false,
-               int ghost_depth = -1) {
-  const Variant& v = kVariants[variant];
-  // ceil(iterations / T) passes of nearly equal size (25 at T = 10 -> 9, 8, 8 rather than 10, 10, 5): the same
-  // number of loads and stores, but narrower halos on every pass
+// The passes of one projection call: ceil(iterations / T) passes of nearly equal size (25 at T = 10 -> 9, 8, 8 rather
+// than 10, 10, 5: the same number of loads and stores, but narrower halos on every pass).  Row window of pass k:
+//   whole domain (ghost_depth < 0, push_sides == 0): every row;
+//   linked slab, deep halo (ghost_depth >= 0): the owned rows plus the ghost rows still exact when the pass starts;
+//   linked slab, push mode (push_sides != 0): the owned rows plus 2 it ghost rows on every side that has a neighbour —
+//   exactly what `it` iterations consume; the pass writes the owned rows only and its edge tiles store the rows
+//   [own_lo, own_lo + halo) / [own_hi - halo, own_hi) into the neighbours' ghost rows as well (PushArgs).
+// run_passes launches this list; the order cache and sayal_debug_pass_plans (the CPU tests of the covering
+// invariants) read the same list.
+struct PassPlan {
+  int iterations, row_lo, row_hi, write_lo, write_hi;
+  int src_lo[2], src_hi[2], n_pushers[2];
+  Geometry q;
+};
+
+int make_pass_plans(const Grid& g, const Variant& v, int T, int iterations, int ghost_depth, int push_sides, int halo,
+                    PassPlan* out, int capacity) {
+  if (iterations <= 0 || T <= 0) return 0;
   const int passes = (iterations + T - 1) / T;
   const int base = iterations / passes, longer = iterations % passes;
-  int done = 0;
-  for (int pass = 0; pass < passes; pass++) {
-    int it = base + (pass < longer ? 1 : 0);
-    // row window: everything, or (linked slab) the owned rows plus the ghost rows still exact before this pass
-    int row_lo = 0, row_hi = s->g.local_rows;
-    if (ghost_depth >= 0) {
+  const int th = v.ry * v.nw;
+  int done = 0, n = 0;
+  for (int pass = 0; pass < passes && n < capacity; pass++) {
+    PassPlan p = {};
+    p.iterations = base + (pass < longer ? 1 : 0);
+    p.row_lo = 0;
+    p.row_hi = g.local_rows;
+    if (push_sides) {
+      if (2 * p.iterations > halo) return -1;  // a pass may not consume more ghost rows than a push delivers
+      if (push_sides & 1) p.row_lo = g.own_lo - 2 * p.iterations < 0 ? 0 : g.own_lo - 2 * p.iterations;
+      if (push_sides & 2) p.row_hi = g.own_hi + 2 * p.iterations > g.local_rows ? g.local_rows : g.own_hi + 2 * p.iterations;
+    } else if (ghost_depth >= 0) {
       const int depth = ghost_depth - 2 * done;
-      row_lo = s->g.own_lo - depth < 0 ? 0 : s->g.own_lo - depth;
-      row_hi = s->g.own_hi + depth > s->g.local_rows ? s->g.local_rows : s->g.own_hi + depth;
+      p.row_lo = g.own_lo - depth < 0 ? 0 : g.own_lo - depth;
+      p.row_hi = g.own_hi + depth > g.local_rows ? g.local_rows : g.own_hi + depth;
     }
-    Geometry q;
-    if (!geometry(s->g, v, it, &q, row_hi - row_lo)) return set_error(SAYAL_EINVAL, "projection tile: temporal block too large for the tile");
-    PackArgs a;
+    p.write_lo = (push_sides & 1) ? g.own_lo : p.row_lo;
+    p.write_hi = (push_sides & 2) ? g.own_hi : p.row_hi;
+    if (!geometry(g, v, p.iterations, &p.q, p.row_hi - p.row_lo)) return -1;
+    p.src_lo[0] = g.own_lo; p.src_hi[0] = g.own_lo + halo;
+    p.src_lo[1] = g.own_hi - halo; p.src_hi[1] = g.own_hi;
+    for (int d = 0; d < 2; d++) {
+      p.n_pushers[d] = 0;
+      if (!(push_sides & (1 << d))) continue;
+      for (int ty = 0; ty < p.q.tiles_y; ty++) {  // the kernel's vy0 / vy1 / push0 / push1
+        const int y0 = p.row_lo + ty * p.q.stride_y;
+        int vy0 = y0 == p.row_lo ? p.row_lo : y0 + p.q.halo_y;
+        int vy1 = y0 + th >= p.row_hi ? p.row_hi : y0 + th - p.q.halo_y;
+        if (vy0 < p.write_lo) vy0 = p.write_lo;
+        if (vy1 > p.write_hi) vy1 = p.write_hi;
+        if (vy0 < p.src_hi[d] && vy1 > p.src_lo[d]) p.n_pushers[d] += p.q.tiles_x;
+      }
+    }
+    out[n++] = p;
+    done += p.iterations;
+  }
+  return n;
+}
+
+constexpr int kMaxPasses = 256;
+
+// which sides of a linked slab take pushes (0: the call does not push)
+int push_sides_of(const Sim* s) {
+  if (!s->push_active) return 0;
+  return (s->link.peer_words[0] ? 1 : 0) | (s->link.peer_words[1] ? 2 : 0);
+}
+
+int run_passes(Sim* s, int variant, int T, int iterations, float d_t, bool with_forces = false, bool with_extrap = false,
+               int ghost_depth = -1, int push_sides = 0) {
+  const Variant& v = kVariants[variant];
+  static thread_local PassPlan plans[kMaxPasses];
+  const int passes = make_pass_plans(s->g, v, T, iterations, ghost_depth, push_sides, s->slab_halo, plans, kMaxPasses);
+  if (passes < 0 || passes != (iterations + T - 1) / T)
+    return set_error(SAYAL_EINVAL, push_sides ? "projection tile: temporal block too large for the tile or the slab's halo"
+                                              : "projection tile: temporal block too large for the tile");
+  const int signature = (iterations << 8) | passes;
+  for (int pass = 0; pass < passes; pass++) {
+    const PassPlan& pl = plans[pass];
+    const Geometry& q = pl.q;
+    const int it = pl.iterations;
+    PackArgs a = {};
     a.g = s->g;
-    a.row_lo = row_lo;
-    a.row_hi = row_hi;
+    a.row_lo = pl.row_lo;
+    a.row_hi = pl.row_hi;
+    a.write_lo = pl.write_lo;
+    a.write_hi = pl.write_hi;
     a.u_in = s->u;
     a.v_in = s->v;
     a.u_out = s->u_buf;
@@ -788,7 +932,7 @@ int run_passes(Sim* s, int variant, int T, int iterations, float d_t, bool with_
     a.hf = (float)s->g.h;
     a.inv_dt = 1.0f / d_t;
     a.extrap_on = with_extrap && pass == passes - 1;
-    a.force_on = with_forces && done == 0;
+    a.force_on = with_forces && pass == 0;
     a.smoke = s->smoke;
     if (a.force_on) {
       const ForceArgs& f = s->fuse_args;
@@ -798,18 +942,42 @@ int run_passes(Sim* s, int variant, int T, int iterations, float d_t, bool with_
       a.smoke_lo = f.smoke_lo; a.smoke_hi = f.smoke_hi; a.smoke_count = ph.wt_smoke_count;
       a.smoke_height = ph.wt_smoke_height; a.period = f.period; a.anchor = f.anchor;
     }
+    if (push_sides) {
+      PushArgs& pu = a.push;
+      pu.on = push_sides;
+      pu.pass_index = pass;
+      pu.signature = signature;
+      // the neighbour's output arrays of this pass: it ping-pongs in step with us, so its output is the array with
+      // the creation index of ours (0..3 = u, v, u_buf, v_buf as allocated)
+      const int iu = (int)(((char*)s->u_buf - (char*)s->vel_block) / (ptrdiff_t)s->vel_stride);
+      const int iv = (int)(((char*)s->v_buf - (char*)s->vel_block) / (ptrdiff_t)s->vel_stride);
+      for (int d = 0; d < 2; d++) {
+        pu.src_lo[d] = pl.src_lo[d]; pu.src_hi[d] = pl.src_hi[d];
+        pu.dst_row0[d] = s->peer_ghost_row0[d];
+        pu.n_pushers[d] = pl.n_pushers[d];
+        pu.peer_u[d] = s->peer_vel[d][iu];
+        pu.peer_v[d] = s->peer_vel[d][iv];
+        pu.peer_words[d] = s->link.peer_words[d];
+        if ((push_sides & (1 << d)) && (pl.n_pushers[d] <= 0 || !pu.peer_u[d] || !pu.peer_v[d]))
+          return set_error(SAYAL_EINVAL, "projection push: no tile produces the slab's edge rows (slab thinner than its halo?)");
+      }
+      pu.my_words = s->link.my_words;
+      pu.ticket = s->link.push_ticket;
+      pu.step_seq = s->link.step_seq;
+      pu.link_error = s->link.link_error;
+    }
     a.timeline = s->d_timeline;  // the last pass wins: profile single passes
     if (s->d_timeline && (size_t)q.tiles_x * q.tiles_y * 5 > s->timeline_cap) a.timeline = nullptr;
     s->timeline_tiles = a.timeline ? q.tiles_x * q.tiles_y : 0;
     a.tiles_x = q.tiles_x;
-    a.order = tile_order(s, variant, it, q, row_lo, row_hi);
+    a.order = tile_order(s, variant, it, q, pl.row_lo, pl.row_hi, push_sides);
     int r = launch_pass(s, v, a, dim3(q.tiles_x * q.tiles_y), s->stream);
     if (r != SAYAL_OK) return r;
     float* t = s->u; s->u = s->u_buf; s->u_buf = t;  // ping-pong: neighbouring tiles still read the old halo
     t = s->v; s->v = s->v_buf; s->v_buf = t;
     s->parity ^= 1;
-    done += it;
   }
+  if (push_sides) return launch_slab_push_wait(s, passes, signature);
   return SAYAL_OK;
 }
 
@@ -837,12 +1005,17 @@ int tiled_preload() {
 // every candidate produces the same bits, so the choice never changes results).
 int tiled_prepare(Sim* s, int iterations) {
   if (iterations <= 0) return SAYAL_OK;
+  const int push = push_sides_of(s) ? 1 : 0;
   for (int k = 0; k < s->n_plans; k++)
-    if (s->plans[k].iterations == iterations) {  // slab runs alternate between chunk sizes: keep every plan
+    if (s->plans[k].iterations == iterations && s->plans[k].push == push) {  // slab runs alternate between chunk sizes: keep every plan
       s->plan_variant = s->plans[k].variant;
       s->plan_T = s->plans[k].T;
       return SAYAL_OK;
     }
+  // the temporal block is given (option), dictated by the chain (push mode: every rank must split alike), or tuned
+  int forced_T = 0;
+  if (s->temporal_block > 0) forced_T = s->temporal_block < iterations ? s->temporal_block : iterations;
+  else if (push) forced_T = tiled_push_temporal_block(iterations, s->slab_halo);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
   struct Cand { int variant, T; double cost; float ms; };
@@ -850,11 +1023,11 @@ int tiled_prepare(Sim* s, int iterations) {
   int nc = 0;
   for (int v = 0; v < kNumVariants; v++)
     for (int T = 1; T <= kMaxT && T <= iterations; T++) {
-      if (s->temporal_block > 0 && T != (s->temporal_block < iterations ? s->temporal_block : iterations)) continue;
+      if (forced_T > 0 && T != forced_T) continue;
       if (s->force_variant >= 0 && v != s->force_variant) continue;
       {  // run_passes splits evenly: T and ceil(n / passes(T)) describe the same plan, keep the canonical one
         int passes = (iterations + T - 1) / T;
-        if (s->temporal_block <= 0 && (iterations + passes - 1) / passes != T) continue;
+        if (forced_T <= 0 && (iterations + passes - 1) / passes != T) continue;
       }
       double c = model_cost(s->g, kVariants[v], T, iterations, sms);
       if (c < 1e29) cands[nc++] = {v, T, c, 0.f};
@@ -864,6 +1037,7 @@ int tiled_prepare(Sim* s, int iterations) {
     for (int b = a + 1; b < nc; b++)
       if (cands[b].cost < cands[a].cost) { Cand t = cands[a]; cands[a] = cands[b]; cands[b] = t; }
   int best = 0;
+  bool timed = false;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(s->stream, &cap);
   // time the model's best 8 candidates always, the rest while the tuning budget (about 0.25 s) lasts
@@ -926,6 +1100,14 @@ int tiled_prepare(Sim* s, int iterations) {
       best = 0;
       for (int c = 1; c < finalists; c++)
         if (cands[c].ms < cands[best].ms) best = c;
+      // Reproducibility: finalists within 1.5 % of the fastest are a tie on this hardware (run-to-run noise is of that
+      // order); among them the plan the model ranks best wins, so the same grid gets the same plan on every box.
+      {
+        const float limit = cands[best].ms * 1.015f;
+        for (int c = 0; c < finalists; c++)
+          if (cands[c].ms <= limit && cands[c].cost < cands[best].cost) best = c;
+      }
+      timed = true;
       // restore state and bookkeeping: tuning is invisible
       s->u = u0; s->v = v0; s->u_buf = ub0; s->v_buf = vb0;
       s->parity = parity;
@@ -944,6 +1126,15 @@ int tiled_prepare(Sim* s, int iterations) {
   }
   s->plan_variant = cands[best].variant;
   s->plan_T = cands[best].T;
+  {  // what was considered, for the bench line and for anyone who wonders why this plan (sayal_plan_log)
+    int at = snprintf(s->plan_log, sizeof s->plan_log, "n=%d %s%s: rows T model ms\n", iterations, timed ? "timed" : "model only",
+                      push ? ", push mode" : "");
+    for (int c = 0; c < nc && at < (int)sizeof s->plan_log - 48; c++) {
+      if (timed && cands[c].ms > 1e29f) continue;
+      at += snprintf(s->plan_log + at, sizeof s->plan_log - at, "%c %d %d %.1f %.4f\n", c == best ? '*' : ' ',
+                     kVariants[cands[c].variant].ry, cands[c].T, cands[c].cost, timed ? cands[c].ms : 0.f);
+    }
+  }
   {  // the issue orders of the plan's pass geometries, now (they cannot be built while a graph is captured)
     const int passes = (iterations + s->plan_T - 1) / s->plan_T;
     for (int it = iterations / passes; it <= (iterations + passes - 1) / passes; it++) {
@@ -952,53 +1143,28 @@ int tiled_prepare(Sim* s, int iterations) {
     }
   }
   if (s->n_plans == Sim::kMaxPlans) s->n_plans = 0;  // full: start over (never happens with <= 8 chunk sizes)
-  s->plans[s->n_plans++] = {iterations, s->plan_variant, s->plan_T};
+  s->plans[s->n_plans++] = {iterations, s->plan_variant, s->plan_T, push};
   return SAYAL_OK;
 }
 
-// The passes of one projection call: ceil(iterations / T) passes of nearly equal size; pass k sweeps the rows that
-// are still exact when it starts (everything when ghost_depth < 0).  run_passes evaluates the same arithmetic
-// pass by pass; this list form serves the order cache and sayal_debug_pass_plans (the CPU tests of the covering
-// invariants).
-struct PassPlan {
-  int iterations, row_lo, row_hi;
-  Geometry q;
-};
-
-int make_pass_plans(const Grid& g, const Variant& v, int T, int iterations, int ghost_depth, PassPlan* out, int capacity) {
-  if (iterations <= 0 || T <= 0) return 0;
-  const int passes = (iterations + T - 1) / T;
-  const int base = iterations / passes, longer = iterations % passes;
-  int done = 0, n = 0;
-  for (int pass = 0; pass < passes && n < capacity; pass++) {
-    PassPlan p;
-    p.iterations = base + (pass < longer ? 1 : 0);
-    p.row_lo = 0;
-    p.row_hi = g.local_rows;
-    if (ghost_depth >= 0) {
-      const int depth = ghost_depth - 2 * done;
-      p.row_lo = g.own_lo - depth < 0 ? 0 : g.own_lo - depth;
-      p.row_hi = g.own_hi + depth > g.local_rows ? g.local_rows : g.own_hi + depth;
-    }
-    if (!geometry(g, v, p.iterations, &p.q, p.row_hi - p.row_lo)) return -1;
-    out[n++] = p;
-    done += p.iterations;
-  }
-  return n;
-}
-
 // Build (outside graph capture) the tile issue orders a linked slab's projection call of `iterations` iterations
-// will use when `ghost_depth` ghost rows are exact at its start: the same pass / window arithmetic as run_passes.
+// will use: the same pass list as run_passes.  ghost_depth: exact ghost rows at the start of a deep-halo call;
+// ignored in push mode (s->push_active).
 int tiled_prepare_windows(Sim* s, int iterations, int ghost_depth) {
   int r = tiled_prepare(s, iterations);
-  if (r != SAYAL_OK || iterations <= 0 || ghost_depth < 0) return r;
-  PassPlan plans[64];
-  const int n = make_pass_plans(s->g, kVariants[s->plan_variant], s->plan_T, iterations, ghost_depth, plans, 64);
-  for (int k = 0; k < n; k++) tile_order(s, s->plan_variant, plans[k].iterations, plans[k].q, plans[k].row_lo, plans[k].row_hi);
+  const int sides = push_sides_of(s);
+  if (r != SAYAL_OK || iterations <= 0 || (ghost_depth < 0 && !sides)) return r;
+  static thread_local PassPlan plans[kMaxPasses];
+  const int n = make_pass_plans(s->g, kVariants[s->plan_variant], s->plan_T, iterations, ghost_depth, sides, s->slab_halo, plans,
+                                kMaxPasses);
+  for (int k = 0; k < n; k++)
+    tile_order(s, s->plan_variant, plans[k].iterations, plans[k].q, plans[k].row_lo, plans[k].row_hi, sides);
   return SAYAL_OK;
 }
 
 // Host-only (no CUDA call): the pass list of a projection on a grid described by numbers, for sayal_debug_pass_plans.
+// ghost_depth >= 0: deep-halo slab; -1: every row; <= -2: push mode with halo = -ghost_depth (a side has a neighbour
+// when the array holds rows beyond the owned ones on that side).
 int tiled_debug_pass_plans(int pitch, int local_rows, int own_lo, int own_hi, int rows_per_warp, int T, int iterations,
                            int ghost_depth, int32_t* out, int capacity) {
   int variant = -1;
@@ -1008,13 +1174,17 @@ int tiled_debug_pass_plans(int pitch, int local_rows, int own_lo, int own_hi, in
     return -1;
   Grid g = {};
   g.W = pitch; g.H = local_rows; g.pitch = pitch; g.local_rows = local_rows; g.own_lo = own_lo; g.own_hi = own_hi; g.h = 1;
-  PassPlan plans[64];
-  const int n = make_pass_plans(g, kVariants[variant], T, iterations, ghost_depth, plans, capacity < 64 ? capacity : 64);
+  static thread_local PassPlan plans[kMaxPasses];
+  const int halo = ghost_depth <= -2 ? -ghost_depth : 0;
+  const int sides = ghost_depth <= -2 ? ((own_lo > 0 ? 1 : 0) | (own_hi < local_rows ? 2 : 0)) : 0;
+  const int n = make_pass_plans(g, kVariants[variant], T, iterations, ghost_depth, sides, halo, plans,
+                                capacity < kMaxPasses ? capacity : kMaxPasses);
   for (int k = 0; k < n; k++) {
     const PassPlan& p = plans[k];
-    const int32_t row[11] = {p.iterations, p.row_lo, p.row_hi, p.q.halo_x, p.q.halo_y, p.q.stride_x, p.q.stride_y,
-                             p.q.tiles_x, p.q.tiles_y, TW, kVariants[variant].ry * kVariants[variant].nw};
-    for (int c = 0; c < 11; c++) out[11 * k + c] = row[c];
+    const int32_t row[15] = {p.iterations, p.row_lo, p.row_hi, p.q.halo_x, p.q.halo_y, p.q.stride_x, p.q.stride_y,
+                             p.q.tiles_x, p.q.tiles_y, TW, kVariants[variant].ry * kVariants[variant].nw,
+                             p.write_lo, p.write_hi, p.n_pushers[0], p.n_pushers[1]};
+    for (int c = 0; c < 15; c++) out[15 * k + c] = row[c];
   }
   return n;
 }
@@ -1027,7 +1197,17 @@ int launch_projection_tiled(Sim* s, int iterations, float d_t) {
   s->fuse_extrap = with_extrap ? 2 : 0;  // 2 = done: the caller skips the extrapolation kernel
   const int depth = s->proj_depth;
   s->proj_depth = -1;
-  return run_passes(s, s->plan_variant, s->plan_T, iterations, d_t, with_forces, with_extrap, depth);
+  return run_passes(s, s->plan_variant, s->plan_T, iterations, d_t, with_forces, with_extrap, depth, push_sides_of(s));
+}
+
+// Push mode: the temporal block every rank of a chain uses for `iterations` iterations with `halo` ghost rows.  It
+// must not depend on anything rank-local (neighbours pair their passes one to one), so it is a function of these
+// two numbers only: the even split of `iterations` into passes of at most min(halo / 2, 8) iterations.
+int tiled_push_temporal_block(int iterations, int halo) {
+  int cap = halo / 2 < 8 ? halo / 2 : 8;
+  if (cap < 1 || iterations <= 0) return 0;
+  const int passes = (iterations + cap - 1) / cap;
+  return (iterations + passes - 1) / passes;
 }
 
 }  // namespace sayal

@@ -40,9 +40,10 @@ static void free_sim(Sim* s) {
   cudaSetDevice(s->device);
   for (int k = 0; k < 4; k++)
     if (s->graph[k]) cudaGraphExecDestroy(s->graph[k]);
-  float* f[] = {s->u, s->v, s->p, s->smoke, s->u_buf, s->v_buf, s->smoke_buf};
+  float* f[] = {s->p, s->smoke, s->smoke_buf};
   for (float* q : f)
     if (q) cudaFree(q);
+  if (s->vel_block) cudaFree(s->vel_block);  // u, v, u_buf, v_buf
   for (int k = 0; k < s->n_orders; k++)
     if (s->orders[k].order) cudaFree(s->orders[k].order);
   if (s->flags) cudaFree(s->flags);
@@ -52,10 +53,16 @@ static void free_sim(Sim* s) {
   if (s->d_range) cudaFree(s->d_range);
   if (s->d_overflow) cudaFree(s->d_overflow);
   if (s->d_timeline) cudaFree(s->d_timeline);
-  for (int k = 0; k < 2; k++)
+  for (int k = 0; k < 2; k++) {
     if (s->ipc_opened[k]) cudaIpcCloseMemHandle(s->ipc_opened[k]);
+    if (s->ipc_opened_vel[k]) cudaIpcCloseMemHandle(s->ipc_opened_vel[k]);
+  }
   if (s->link_block) cudaFree(s->link_block);
   if (s->link_counters) cudaFree(s->link_counters);
+  if (s->h_link_error) cudaFreeHost(s->h_link_error);
+  if (s->h_gate) cudaFreeHost(s->h_gate);
+  if (s->ev_range) cudaEventDestroy(s->ev_range);
+
   for (int k = 0; k < Sim::kFrames; k++) {
     if (s->d_frame[k]) cudaFree(s->d_frame[k]);
     if (s->h_frame[k]) cudaFreeHost(s->h_frame[k]);
@@ -104,6 +111,11 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
     if (slab->global_height != c->height || slab->row0 < 0 || slab->row0 + slab->rows > c->height || slab->halo < 0) {
       delete s;
       return set_error(SAYAL_EINVAL, "sayal_create_slab: slab does not fit the domain");
+    }
+    // the `halo` owned rows next to an interior edge are what a neighbour receives as its ghost rows
+    if (slab->rows < slab->halo && slab->rows != c->height) {
+      delete s;
+      return set_error(SAYAL_EINVAL, "sayal_create_slab: a slab must own at least `halo` rows");
     }
     int lo = slab->row0 - slab->halo, hi = slab->row0 + slab->rows + slab->halo;
     if (lo < 0) lo = 0;
@@ -155,6 +167,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   s->order_tiles = 1;
   s->advect_kernel = 2;
   s->overlap_exchange = 1;
+  s->slab_push = 1;
   s->advect_margin = 16;
   s->autotune = 1;
   s->plan_variant = -1, s->n_plans = 0;
@@ -174,6 +187,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   if (const char* e = getenv("SAYAL_ORDER_TILES")) s->order_tiles = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_SHRINK_WINDOW")) s->shrink_window = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_FUSE_EXTRAPOLATION")) s->fuse_extrapolation = atoi(e) != 0;
+  if (const char* e = getenv("SAYAL_SLAB_PUSH")) s->slab_push = atoi(e) != 0;
 
   auto fail = [&](int code) {
     free_sim(s);
@@ -187,22 +201,32 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
     e = cudaStreamCreateWithPriority(&s->aux_stream, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_range, cudaEventDisableTiming);
     if (e != cudaSuccess) return fail(set_error(SAYAL_ECUDA, cudaGetErrorString(e)));
   }
   size_t bytes = field_elems(s) * sizeof(float);
-  float** fields[] = {&s->u, &s->v, &s->p, &s->smoke, &s->u_buf, &s->v_buf, &s->smoke_buf};
+  float** fields[] = {&s->p, &s->smoke, &s->smoke_buf};
   for (float** f : fields) {
     e = cudaMalloc(f, bytes);
     if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
     cudaMemsetAsync(*f, 0, bytes, s->stream);
   }
+  // u, v and their back buffers: one allocation (one IPC handle for a neighbouring slab), arrays 256-byte aligned
+  s->vel_stride = (bytes + 255) & ~(size_t)255;
+  e = cudaMalloc(&s->vel_block, 4 * s->vel_stride);
+  if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
+  cudaMemsetAsync(s->vel_block, 0, 4 * s->vel_stride, s->stream);
+  {
+    float** vel[] = {&s->u, &s->v, &s->u_buf, &s->v_buf};
+    for (int k = 0; k < 4; k++) *vel[k] = reinterpret_cast<float*>(reinterpret_cast<char*>(s->vel_block) + k * s->vel_stride);
+  }
   // + slack marked solid: the tap (W, j) of the last row reads one byte past the array when pitch == W
   e = cudaMalloc(&s->flags, field_elems(s) + 64);
   if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
   cudaMemsetAsync(s->flags, FL_SOLID, field_elems(s) + 64, s->stream);
-  e = cudaMalloc(&s->d_range, 2 * sizeof(int32_t));
+  e = cudaMalloc(&s->d_range, 4 * sizeof(int32_t));
   if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
-  cudaMemsetAsync(s->d_range, 0, 2 * sizeof(int32_t), s->stream);  // min = max = 0 until the first step (fluid.cuh:61-62 are uninitialised there)
+  cudaMemsetAsync(s->d_range, 0, 4 * sizeof(int32_t), s->stream);  // min = max = 0 until the first step (fluid.cuh:61-62 are uninitialised there)
   e = cudaMalloc(&s->d_overflow, sizeof(int32_t));
   if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
   cudaMemsetAsync(s->d_overflow, 0, sizeof(int32_t), s->stream);
@@ -314,6 +338,7 @@ static int advect_linked(Sim* s, float d_t, bool smoke, int ghost, int exchange_
 }
 
 bool is_linked(const Sim* s);
+bool push_mode(const Sim* s);
 
 static int step_impl(Sim* s, const sayal_source* src, float d_t) {
   const bool linked = is_linked(s);
@@ -345,6 +370,16 @@ static int step_impl(Sim* s, const sayal_source* src, float d_t) {
   if (!linked) {
     s->fuse_extrap = fold_extrap && !(skip & 2);
     if (!(skip & 16)) TRY(projection(s, s->cfg.proj_n, d_t));
+  } else if (push_mode(s)) {
+    // Push mode: every pass consumes 2 it ghost rows and its edge tiles store the slab's new edge rows straight into
+    // the neighbours' ghost rows (projection_pack.cu), so the whole projection is ONE call with thin windows and the
+    // ghost rows are exact to the full halo again when it returns.
+    s->fuse_extrap = fold_extrap;
+    s->push_active = 1;
+    int r = (skip & 16) ? SAYAL_OK : projection(s, s->cfg.proj_n, d_t);
+    s->push_active = 0;
+    if (r != SAYAL_OK) return r;
+    D = s->slab_halo;
   } else {
     for (int done = 0; done < s->cfg.proj_n;) {
       if (D < 2) {
@@ -360,9 +395,17 @@ static int step_impl(Sim* s, const sayal_source* src, float d_t) {
       done += k;
     }
   }
+  bool range_forked = false;
   if (s->ph.enable_pressure) {
     TRY(launch_pressure_range(s));
     s->range_valid = false;
+    if (linked) {  // one min / max for the whole frame: chain reduction on the aux stream, joined at the end of the step
+      CUDA_TRY(cudaEventRecord(s->ev_range, s->stream));
+      CUDA_TRY(cudaStreamWaitEvent(s->aux_stream, s->ev_range, 0));
+      TRY(launch_slab_range_reduce(s, s->aux_stream));
+      CUDA_TRY(cudaEventRecord(s->ev_range, s->aux_stream));
+      range_forked = true;
+    }
   }
   if (s->fuse_extrap != 2 && !(skip & 2)) TRY(launch_extrapolation(s));
   s->fuse_extrap = 0;
@@ -390,11 +433,31 @@ static int step_impl(Sim* s, const sayal_source* src, float d_t) {
     s->g.valid_hi = s->g.local_rows;
     if (r != SAYAL_OK) return r;
   }
+  if (range_forked) CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_range, 0));
   return SAYAL_OK;
 }
 
 static bool is_slab(const Sim* s) { return s->g.local_rows != s->g.H; }
 bool is_linked(const Sim* s) { return s->link_block && (s->link.peer_recv[0] || s->link.peer_recv[1]); }
+
+// Do the projection passes of a linked step push their edge rows themselves?  Needs the tiled kernel, the
+// neighbours' velocity arrays (every link made through this library has them) and at least two ghost rows.
+bool push_mode(const Sim* s) {
+  if (!is_linked(s) || !s->slab_push || s->projection_kernel != 1 || s->cfg.proj_n <= 0 || s->slab_halo < 2) return false;
+  for (int d = 0; d < 2; d++)
+    if (s->link.peer_words[d] && !s->peer_vel[d][0]) return false;
+  return true;
+}
+
+// The sticky link error of a slab sim (mapped host word, written by the kernels), as an error code.
+static int link_status(const Sim* s, const char* where) {
+  if (!s->h_link_error || *reinterpret_cast<volatile int*>(s->h_link_error) == LINK_OK) return SAYAL_OK;
+  char m[256];
+  snprintf(m, sizeof m, "%s: slab link broken (%s); fields are not valid", where,
+           *s->h_link_error == LINK_PLAN_MISMATCH ? "neighbours split the projection into different passes"
+                                                  : "a neighbour did not answer within 2 s");
+  return set_error(SAYAL_ELINK, m);
+}
 
 }  // namespace sayal
 
@@ -431,6 +494,7 @@ int sayal_step(sayal_sim* sim, const sayal_source* src, float d_t) {
   Sim* s = S(sim);
   if (is_slab(s) && !is_linked(s)) return set_error(SAYAL_EINVAL, "sayal_step: a slab sim must be linked to its neighbours first (sayal_slab_ipc_connect / sayal_slab_connect_local), or stepped stage by stage");
   if (is_linked(s) && s->slab_halo < s->advect_margin + 1) return set_error(SAYAL_EINVAL, "sayal_step: linked slabs need halo >= advect_margin + 1 (default 17)");
+  TRY(link_status(s, "sayal_step"));
   CUDA_TRY(cudaSetDevice(s->device));
   s->steps_done++;
   return step_impl(s, src, d_t);
@@ -447,9 +511,15 @@ int sayal_run(sayal_sim* sim, int32_t steps, float d_t) {
     invalidate_graphs(s);
     s->graph_dt = d_t;
   }
+  TRY(link_status(s, "sayal_run"));
   if (s->projection_kernel == 1) {  // timing is not capturable: choose every plan the step will use first
     if (!is_linked(s)) {
       TRY(tiled_prepare(s, s->cfg.proj_n));
+    } else if (push_mode(s)) {
+      s->push_active = 1;
+      int r = tiled_prepare_windows(s, s->cfg.proj_n, -1);
+      s->push_active = 0;
+      if (r != SAYAL_OK) return r;
     } else {
       int D = s->slab_halo;
       for (int done = 0; done < s->cfg.proj_n;) {  // the chunk sizes step_impl will use
@@ -503,7 +573,7 @@ int sayal_run(sayal_sim* sim, int32_t steps, float d_t) {
 int sayal_sync(sayal_sim* sim) {
   if (!sim) return set_error(SAYAL_EINVAL, "sayal_sync: null sim");
   CUDA_TRY(cudaStreamSynchronize(S(sim)->stream));
-  return SAYAL_OK;
+  return link_status(S(sim), "sayal_sync");
 }
 
 
@@ -546,6 +616,81 @@ int sayal_get_field(sayal_sim* sim, int32_t field, void* host_dst) {
   if (src_pitch == row_bytes) CUDA_TRY(cudaMemcpyAsync(host_dst, src, row_bytes * rows, cudaMemcpyDeviceToHost, s->stream));
   else CUDA_TRY(cudaMemcpy2DAsync(host_dst, row_bytes, src, src_pitch, row_bytes, rows, cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return link_status(s, "sayal_get_field");
+}
+
+// Batched forms of the two calls above: every copy is enqueued on the sim's stream back to back and the call waits
+// once (sayal_get_fields) or not at all beyond what the runtime needs (sayal_set_fields with pinned memory returns
+// when the copies are enqueued; the caller must keep the buffers untouched until sayal_sync or any synchronous call).
+static int copy_field(Sim* s, int field, void* host, bool to_host) {
+  void* p = nullptr;
+  size_t elem;
+  bool dense;
+  TRY(field_info(s, field, &p, &elem, &dense));
+  const size_t dev_pitch = (dense ? s->g.W : s->g.pitch) * elem;
+  char* dev = (char*)p + (size_t)s->g.own_lo * dev_pitch;
+  const size_t row_bytes = s->g.W * elem, rows = s->g.own_hi - s->g.own_lo;
+  if (to_host) {
+    if (dev_pitch == row_bytes) CUDA_TRY(cudaMemcpyAsync(host, dev, row_bytes * rows, cudaMemcpyDeviceToHost, s->stream));
+    else CUDA_TRY(cudaMemcpy2DAsync(host, row_bytes, dev, dev_pitch, row_bytes, rows, cudaMemcpyDeviceToHost, s->stream));
+  } else {
+    if (dev_pitch == row_bytes) CUDA_TRY(cudaMemcpyAsync(dev, host, row_bytes * rows, cudaMemcpyHostToDevice, s->stream));
+    else CUDA_TRY(cudaMemcpy2DAsync(dev, dev_pitch, host, row_bytes, row_bytes, rows, cudaMemcpyHostToDevice, s->stream));
+  }
+  return SAYAL_OK;
+}
+
+// Device-to-device forms for a caller that already lives on the GPU (a renderer, a torch tensor): `dev` holds the
+// owned rows in the reference layout (row pitch W), on the same device; ordered on the sim's stream, asynchronous.
+static int copy_field_device(Sim* s, int field, void* dev_buf, bool to_buf) {
+  void* p = nullptr;
+  size_t elem;
+  bool dense;
+  TRY(field_info(s, field, &p, &elem, &dense));
+  const size_t dev_pitch = (dense ? s->g.W : s->g.pitch) * elem;
+  char* mine = (char*)p + (size_t)s->g.own_lo * dev_pitch;
+  const size_t row_bytes = s->g.W * elem, rows = s->g.own_hi - s->g.own_lo;
+  if (to_buf) CUDA_TRY(cudaMemcpy2DAsync(dev_buf, row_bytes, mine, dev_pitch, row_bytes, rows, cudaMemcpyDeviceToDevice, s->stream));
+  else CUDA_TRY(cudaMemcpy2DAsync(mine, dev_pitch, dev_buf, row_bytes, row_bytes, rows, cudaMemcpyDeviceToDevice, s->stream));
+  return SAYAL_OK;
+}
+
+int sayal_get_field_device(sayal_sim* sim, int32_t field, void* dev_dst) {
+  if (!sim || !dev_dst) return set_error(SAYAL_EINVAL, "sayal_get_field_device: null argument");
+  Sim* s = S(sim);
+  CUDA_TRY(cudaSetDevice(s->device));
+  return copy_field_device(s, field, dev_dst, true);
+}
+
+int sayal_set_field_device(sayal_sim* sim, int32_t field, const void* dev_src) {
+  if (!sim || !dev_src) return set_error(SAYAL_EINVAL, "sayal_set_field_device: null argument");
+  if (field < SAYAL_U || field > SAYAL_SMOKE) return set_error(SAYAL_EINVAL, "sayal_set_field_device: only U, V, P, SMOKE are writable");
+  Sim* s = S(sim);
+  CUDA_TRY(cudaSetDevice(s->device));
+  return copy_field_device(s, field, const_cast<void*>(dev_src), false);
+}
+
+int sayal_get_fields(sayal_sim* sim, int32_t n, const int32_t* fields, void* const* host_dsts) {
+  if (!sim || n < 0 || (n > 0 && (!fields || !host_dsts))) return set_error(SAYAL_EINVAL, "sayal_get_fields: bad argument");
+  Sim* s = S(sim);
+  CUDA_TRY(cudaSetDevice(s->device));
+  for (int k = 0; k < n; k++) {
+    if (!host_dsts[k]) return set_error(SAYAL_EINVAL, "sayal_get_fields: null destination");
+    TRY(copy_field(s, fields[k], host_dsts[k], true));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return link_status(s, "sayal_get_fields");
+}
+
+int sayal_set_fields(sayal_sim* sim, int32_t n, const int32_t* fields, const void* const* host_srcs) {
+  if (!sim || n < 0 || (n > 0 && (!fields || !host_srcs))) return set_error(SAYAL_EINVAL, "sayal_set_fields: bad argument");
+  Sim* s = S(sim);
+  CUDA_TRY(cudaSetDevice(s->device));
+  for (int k = 0; k < n; k++) {
+    if (!host_srcs[k]) return set_error(SAYAL_EINVAL, "sayal_set_fields: null source");
+    if (fields[k] < SAYAL_U || fields[k] > SAYAL_SMOKE) return set_error(SAYAL_EINVAL, "sayal_set_fields: only U, V, P, SMOKE are writable");
+    TRY(copy_field(s, fields[k], const_cast<void*>(host_srcs[k]), false));
+  }
   return SAYAL_OK;
 }
 
@@ -598,7 +743,9 @@ int sayal_pressure_range(sayal_sim* sim, float* min_p, float* max_p) {
   if (!s->range_valid) {
     int32_t r[2];
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    CUDA_TRY(cudaMemcpy(r, s->d_range, sizeof r, cudaMemcpyDeviceToHost));
+    TRY(link_status(s, "sayal_pressure_range"));
+    // linked slabs: the range of the whole domain (reduced along the chain by the step), like the reference's one pair
+    CUDA_TRY(cudaMemcpy(r, s->d_range + (is_linked(s) ? 2 : 0), sizeof r, cudaMemcpyDeviceToHost));
     s->min_p = from_ordered(r[0]);
     s->max_p = from_ordered(r[1]);
     s->range_valid = true;
@@ -822,6 +969,9 @@ int sayal_set_option(sayal_sim* sim, const char* key, int64_t value) {
     s->fuse_extrapolation = value != 0;
   } else if (!strcmp(key, "shrink_window")) {
     s->shrink_window = value != 0;
+  } else if (!strcmp(key, "slab_push")) {
+    s->slab_push = value != 0;
+    s->plan_variant = -1, s->n_plans = 0;
   } else if (!strcmp(key, "order_tiles")) {
     s->order_tiles = value != 0;
     s->plan_variant = -1, s->n_plans = 0;
@@ -851,6 +1001,8 @@ int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value) {
   else if (!strcmp(key, "fuse_forces")) *value = s->fuse_forces;
   else if (!strcmp(key, "order_tiles")) *value = s->order_tiles;
   else if (!strcmp(key, "shrink_window")) *value = s->shrink_window;
+  else if (!strcmp(key, "slab_push")) *value = s->slab_push;
+  else if (!strcmp(key, "push_mode")) *value = push_mode(s) ? 1 : 0;
   else if (!strcmp(key, "fuse_extrapolation")) *value = s->fuse_extrapolation;
   else if (!strcmp(key, "advect_kernel")) *value = s->advect_kernel;
   else if (!strcmp(key, "autotune")) *value = s->autotune;
@@ -867,7 +1019,7 @@ int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value) {
     if (s->link_block) {
       CUDA_TRY(cudaSetDevice(s->device));
       CUDA_TRY(cudaStreamSynchronize(s->stream));
-      CUDA_TRY(cudaMemcpy(&v, s->link.link_error, sizeof v, cudaMemcpyDeviceToHost));
+      v = *reinterpret_cast<volatile int*>(s->h_link_error);
     }
     *value = v;
   } else if (!strcmp(key, "pitch")) *value = s->g.pitch;
@@ -876,6 +1028,18 @@ int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value) {
   else if (!strcmp(key, "own_hi")) *value = s->g.own_hi;
   else return set_error(SAYAL_EINVAL, "sayal_get_option: unknown key");
   return SAYAL_OK;
+}
+
+int sayal_plan_log(sayal_sim* sim, char* buf, int32_t capacity) {
+  if (!sim) return set_error(SAYAL_EINVAL, "sayal_plan_log: null sim");
+  Sim* s = S(sim);
+  const int n = (int)strlen(s->plan_log);
+  if (buf && capacity > 0) {
+    const int m = n < capacity - 1 ? n : capacity - 1;
+    std::memcpy(buf, s->plan_log, m);
+    buf[m] = 0;
+  }
+  return n;
 }
 
 int sayal_debug_timeline(sayal_sim* sim, int64_t* host_dst, int32_t max_tiles, int32_t* n_tiles) {
@@ -910,13 +1074,50 @@ int sayal_stream_delay(sayal_sim* sim, int64_t microseconds) {
   return SAYAL_OK;
 }
 
+// Host-released gate: a one-thread kernel on the sim's stream spins on a word in mapped host memory until
+// sayal_stream_release stores the matching ticket.  Everything enqueued behind it starts exactly when the host says
+// so — a measured region can be enqueued completely, the ranks of a multi-GPU run can meet at a host barrier, and
+// only then do the devices begin.  The spin gives up after 20 s (a forgotten release must not wedge the GPU).
+__global__ void stream_gate_kernel(const volatile unsigned* gate, unsigned ticket) {
+  long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while ((int)(*gate - ticket) < 0) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > 20000000000ll) break;
+    __nanosleep(200);
+  }
+}
+
+int sayal_stream_hold(sayal_sim* sim) {
+  if (!sim) return set_error(SAYAL_EINVAL, "sayal_stream_hold: null sim");
+  Sim* s = S(sim);
+  CUDA_TRY(cudaSetDevice(s->device));
+  if (!s->h_gate) {
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&s->h_gate), sizeof(unsigned), cudaHostAllocMapped));
+    *s->h_gate = 0;
+    CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&s->d_gate), s->h_gate, 0));
+  }
+  s->gate_ticket++;
+  stream_gate_kernel<<<1, 1, 0, s->stream>>>(s->d_gate, s->gate_ticket);
+  CUDA_TRY(cudaGetLastError());
+  return SAYAL_OK;
+}
+
+int sayal_stream_release(sayal_sim* sim) {
+  if (!sim) return set_error(SAYAL_EINVAL, "sayal_stream_release: null sim");
+  Sim* s = S(sim);
+  if (!s->h_gate) return set_error(SAYAL_EINVAL, "sayal_stream_release: no gate was set");
+  __atomic_store_n(s->h_gate, s->gate_ticket, __ATOMIC_RELEASE);
+  return SAYAL_OK;
+}
+
 int sayal_debug_pass_plans(int32_t pitch, int32_t local_rows, int32_t own_lo, int32_t own_hi, int32_t rows_per_warp,
                            int32_t temporal_block, int32_t iterations, int32_t ghost_depth, int32_t* out, int32_t capacity,
                            int32_t* n_passes) {
   if (!out || !n_passes || capacity < 1) return set_error(SAYAL_EINVAL, "sayal_debug_pass_plans: null argument");
   int n = tiled_debug_pass_plans(pitch, local_rows, own_lo, own_hi, rows_per_warp, temporal_block, iterations, ghost_depth,
                                  out, capacity);
-  if (n < 0) return set_error(SAYAL_EINVAL, "sayal_debug_pass_plans: no such plan (rows per warp 8/10/12, T 1..16, pitch % 4 == 0)");
+  if (n < 0) return set_error(SAYAL_EINVAL, "sayal_debug_pass_plans: no such plan (rows per warp 8/10/12, T 1..16, pitch % 4 == 0, push mode: 2 T <= halo)");
   *n_passes = n;
   return SAYAL_OK;
 }
@@ -925,41 +1126,60 @@ int64_t sayal_launch_count(sayal_sim* sim) { return sim ? S(sim)->launches : 0; 
 void* sayal_stream(sayal_sim* sim) { return sim ? (void*)S(sim)->stream : nullptr; }
 
 // ---- slab links ---------------------------------------------------------------------------------------
-int sayal_slab_ipc_export(sayal_sim* sim, void* handle_out, int64_t* stage_elems) {
+static_assert(sizeof(LinkInfo) <= SAYAL_LINK_INFO_BYTES, "LinkInfo must fit the opaque blob of sayal.h");
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+
+int sayal_slab_ipc_export(sayal_sim* sim, void* info_out) {
   STAGE_PROLOGUE("sayal_slab_ipc_export");
-  if (!handle_out || !stage_elems) return set_error(SAYAL_EINVAL, "sayal_slab_ipc_export: null argument");
-  TRY(slab_link_alloc(s));
+  if (!info_out) return set_error(SAYAL_EINVAL, "sayal_slab_ipc_export: null argument");
+  LinkInfo info;
+  TRY(slab_link_export(s, &info));
   cudaIpcMemHandle_t h;
   CUDA_TRY(cudaIpcGetMemHandle(&h, s->link_block));
-  static_assert(sizeof(h) == SAYAL_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
-  std::memcpy(handle_out, &h, sizeof h);
-  *stage_elems = (int64_t)slab_link_stage_elems(s);
+  std::memcpy(info.link_handle, &h, sizeof h);
+  CUDA_TRY(cudaIpcGetMemHandle(&h, s->vel_block));
+  std::memcpy(info.vel_handle, &h, sizeof h);
+  std::memset(info_out, 0, SAYAL_LINK_INFO_BYTES);
+  std::memcpy(info_out, &info, sizeof info);
   return SAYAL_OK;
 }
 
-int sayal_slab_ipc_connect(sayal_sim* sim, int32_t side, const void* handle, int64_t stage_elems) {
+int sayal_slab_ipc_connect(sayal_sim* sim, int32_t side, const void* info_in) {
   STAGE_PROLOGUE("sayal_slab_ipc_connect");
-  if (!handle || (side != 0 && side != 1)) return set_error(SAYAL_EINVAL, "sayal_slab_ipc_connect: bad argument");
+  if (!info_in || (side != 0 && side != 1)) return set_error(SAYAL_EINVAL, "sayal_slab_ipc_connect: bad argument");
+  if (s->ipc_opened[side]) return set_error(SAYAL_EINVAL, "sayal_slab_ipc_connect: that side is already connected");
+  LinkInfo info;
+  std::memcpy(&info, info_in, sizeof info);
   cudaIpcMemHandle_t h;
-  std::memcpy(&h, handle, sizeof h);
-  void* p = nullptr;
+  void *p = nullptr, *pv = nullptr;
+  std::memcpy(&h, info.link_handle, sizeof h);
   CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-  int r = slab_link_connect(s, side, p, (size_t)stage_elems);
+  std::memcpy(&h, info.vel_handle, sizeof h);
+  cudaError_t e = cudaIpcOpenMemHandle(&pv, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    cudaIpcCloseMemHandle(p);
+    return set_error(SAYAL_ECUDA, cudaGetErrorString(e));
+  }
+  int r = slab_link_connect_info(s, side, &info, p, pv);
   if (r != SAYAL_OK) {
     cudaIpcCloseMemHandle(p);
+    cudaIpcCloseMemHandle(pv);
     return r;
   }
   s->ipc_opened[side] = p;
+  s->ipc_opened_vel[side] = pv;
   invalidate_graphs(s);
+  s->plan_variant = -1, s->n_plans = 0;  // linked slabs tune their plans under the chain's constraints
   return SAYAL_OK;
 }
 
 int sayal_slab_connect_local(sayal_sim* sim, int32_t side, sayal_sim* neighbour) {
   STAGE_PROLOGUE("sayal_slab_connect_local");
-  if (!neighbour) return set_error(SAYAL_EINVAL, "sayal_slab_connect_local: null neighbour");
+  if (!neighbour || (side != 0 && side != 1)) return set_error(SAYAL_EINVAL, "sayal_slab_connect_local: bad argument");
   Sim* n = S(neighbour);
   CUDA_TRY(cudaSetDevice(n->device));
-  TRY(slab_link_alloc(n));
+  LinkInfo info;
+  TRY(slab_link_export(n, &info));
   CUDA_TRY(cudaSetDevice(s->device));
   if (n->device != s->device) {
     int can = 0;
@@ -969,8 +1189,9 @@ int sayal_slab_connect_local(sayal_sim* sim, int32_t side, sayal_sim* neighbour)
     if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return set_error(SAYAL_ECUDA, cudaGetErrorString(e));
     cudaGetLastError();
   }
-  TRY(slab_link_connect(s, side, n->link_block, slab_link_stage_elems(n)));
+  TRY(slab_link_connect_info(s, side, &info, n->link_block, n->vel_block));
   invalidate_graphs(s);
+  s->plan_variant = -1, s->n_plans = 0;
   return SAYAL_OK;
 }
 

@@ -66,14 +66,67 @@ struct ForceArgs {
 };
 
 // Device-side view of a slab's links to its two neighbours (slab_exchange.cu); side 0 = low memory rows.
+// Every sim owns one neighbour-writable block: 64 control words followed by the receive areas.  Control words:
+//   [0], [1]   exchange flags: sequence number of the last exchange the neighbour on that side has pushed
+//   [2], [3]   pass flags (projection passes that push their edge rows themselves, projection_pack.cu)
+//   [4], [5]   plan signature of the neighbour's pushes (cross-check: both sides must split the projection alike)
+//   [8..10]    pressure range travelling down the chain (from side 0): sequence, ordered min, ordered max
+//   [12..14]   global pressure range travelling back up (from side 1)
+enum : int { LW_XFLAG = 0, LW_PFLAG = 2, LW_PITER = 4, LW_RANGE_DOWN = 8, LW_RANGE_UP = 12, LW_WORDS = 64 };
+// link_error values (sticky; the first one wins)
+enum : int { LINK_OK = 0, LINK_TIMEOUT = 1, LINK_PLAN_MISMATCH = 2 };
+
+#ifdef __CUDACC__
+// system-scope flag primitives of the neighbour protocols (slab_exchange.cu, projection_pack.cu)
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ long long now_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr long long kSpinLimitNs = 2000000000ll;
+// Spin until *word >= target (wrap-safe).  Gives up after two seconds, or at once when the link is already broken,
+// raising the sticky error word; returns false then.
+__device__ __forceinline__ bool spin_until(const unsigned* word, unsigned target, int* link_error) {
+  if ((int)(ld_acquire_sys(word) - target) >= 0) return true;
+  const long long t0 = now_ns();
+  while ((int)(ld_acquire_sys(word) - target) < 0) {
+    if (now_ns() - t0 > kSpinLimitNs || *reinterpret_cast<volatile int*>(link_error) != 0) {
+      atomicCAS(link_error, 0, 1);
+      __threadfence_system();
+      return false;
+    }
+  }
+  return true;
+}
+#endif
+
 struct SlabLinkDev {
   float* peer_recv[2];    // where my edge rows land in the neighbour's block (null: no neighbour on that side)
-  unsigned* peer_flag[2]; // the neighbour's flag word for my pushes
+  unsigned* peer_words[2];// the neighbour's control words
   float* my_recv[2];      // where the neighbours' rows land here (2 parities each)
-  unsigned* my_flag;      // [2], written by the neighbours
+  unsigned* my_words;     // my control words, written by the neighbours
   unsigned *send_seq, *recv_seq, *ticket;  // private counters, advanced by the kernels
-  int* link_error;        // raised when a wait gave up
+  unsigned *range_seq, *step_seq, *push_ticket;
+  int* link_error;        // mapped host word, raised when a wait gave up (sticky: later waits return at once)
   size_t stage_elems;     // floats per receive buffer: halo * W * 3
+};
+
+// What two neighbouring slabs tell each other once (opaque to callers: SAYAL_LINK_INFO_BYTES of include/sayal.h).
+struct LinkInfo {
+  unsigned char link_handle[64];  // cudaIpcMemHandle_t of the link block
+  unsigned char vel_handle[64];   // cudaIpcMemHandle_t of the velocity block
+  int64_t stage_elems;
+  int64_t vel_stride;             // bytes between the four velocity arrays
+  int32_t W, pitch, local_rows, own_lo, own_hi, halo, advect_margin, parity;
+  int32_t row_base, global_height, abi, reserved;
 };
 
 struct Sim {
@@ -82,12 +135,17 @@ struct Sim {
   Phys ph;
   int device;
   cudaStream_t stream;
-  // fp32 fields, local_rows x pitch
+  // fp32 fields, local_rows x pitch.  u, v and their back buffers live in ONE allocation (vel_block: four arrays
+  // vel_stride bytes apart, in the order u, v, u_buf, v_buf as created) so that a neighbouring slab can map all of
+  // them with one IPC handle and store its edge rows straight into our ghost rows (projection_pack.cu).
   float *u, *v, *p, *smoke, *u_buf, *v_buf, *smoke_buf;
+  void* vel_block;
+  size_t vel_stride;
   uint8_t* flags;
   uint16_t* geo;                    // static per-cell geometry word of the tile advection (advect_tile.cu)
   int32_t *d_is_solid, *d_total_s;  // built on demand for get_field / device_ptr
-  int32_t* d_range;                 // ordered-int min / max of pressure
+  int32_t* d_range;                 // ordered-int min / max of pressure: [0], [1] of the owned rows; [2], [3] of the
+                                    // whole domain (linked slabs: reduced along the chain, slab_exchange.cu)
   int32_t* d_overflow;              // count of back-traces that left the local rows (slab runs)
   long long* d_timeline;            // profiling only: per-CTA phase timestamps of the last projection pass
   size_t timeline_cap;              // capacity in int64
@@ -112,12 +170,13 @@ struct Sim {
   int force_variant;      // -1 = any tile variant
   int plan_variant, plan_T;  // tile plan of the last projection (projection_pack.cu)
   static constexpr int kMaxPlans = 8;
-  struct Plan { int iterations, variant, T; } plans[kMaxPlans];  // one per iteration count seen
+  struct Plan { int iterations, variant, T, push; } plans[kMaxPlans];  // one per iteration count seen
   int n_plans;
+  char plan_log[2048];     // candidates of the last tuning (sayal_plan_log)
   // issue order of the tiles (most expensive first) per tile geometry, built on first use (projection_pack.cu)
   int order_tiles;        // option (default 1)
   static constexpr int kMaxOrders = 64;
-  struct TileOrder { int variant, it, row_lo, row_hi; int* order; } orders[kMaxOrders];
+  struct TileOrder { int variant, it, row_lo, row_hi, edge_first; int* order; } orders[kMaxOrders];
   int n_orders;
   // CUDA graph cache for sayal_run: one single-step graph per starting buffer parity, with the
   // pointer assignment the step leaves behind (the step swaps front and back buffers)
@@ -129,10 +188,24 @@ struct Sim {
   int64_t launches;
   // y-slab links (slab_exchange.cu)
   int slab_halo;            // ghost rows per interior side as requested at creation (0: whole domain)
-  void* link_block;         // neighbour-writable block (flags + receive areas), IPC-exportable
+  void* link_block;         // neighbour-writable block (control words + receive areas), IPC-exportable
   unsigned* link_counters;  // private
   SlabLinkDev link;
-  void* ipc_opened[2];      // peer blocks opened with cudaIpcOpenMemHandle (closed on destroy)
+  int* h_link_error;        // host view of link.link_error (cudaHostAlloc, mapped): read after a sync at no cost
+  void* ipc_opened[2];      // peer link blocks opened with cudaIpcOpenMemHandle (closed on destroy)
+  void* ipc_opened_vel[2];  // peer velocity blocks, likewise
+  // in-pass push (projection_pack.cu): the neighbours' four velocity arrays as addressable from this device, in
+  // their creation order, and where my edge rows land in them
+  float* peer_vel[2][4];
+  int peer_ghost_row0[2];   // local row (in the neighbour's arrays) of the first row I push to that side
+  int slab_push;            // option (default 1): projection passes push their edge rows themselves, one thin
+                            // exchange per pass instead of a deep halo recomputed through the whole step
+  int push_active;          // set by step_impl for the projection call it is about to make
+  cudaEvent_t ev_range;     // the chain reduction of the pressure range runs on aux_stream
+  // host-released gate (sayal_stream_hold / sayal_stream_release): a one-thread kernel spinning on a mapped word
+  unsigned* h_gate;
+  unsigned* d_gate;
+  unsigned gate_ticket;     // value the next release writes
   cudaStream_t aux_stream;  // exchange kernels run here, concurrently with interior compute
   cudaEvent_t ev_fork, ev_join;
   int overlap_exchange;     // option: overlap exchanges with interior compute (default 1)
@@ -149,6 +222,9 @@ struct Sim {
   int frame_head, frame_pending;  // next slot to submit into, frames submitted and not yet acquired
   bool frame_used[kFrames];       // ev_copied[k] has been recorded at least once
 };
+
+bool is_linked(const Sim* s);  // sayal_api.cu: the slab has at least one neighbour
+bool push_mode(const Sim* s);  // projection passes push their edge rows themselves (projection_pack.cu)
 
 // ---- kernels_basic.cu ---------------------------------------------------------------------------
 int launch_build_flags(Sim* s);
@@ -170,10 +246,14 @@ int launch_advect_geo_rows(Sim* s, float d_t, bool smoke, int row_lo, int row_hi
 
 // ---- slab_exchange.cu -----------------------------------------------------------------------------
 int slab_link_alloc(Sim* s);
-int slab_link_connect(Sim* s, int side, void* peer_block, size_t peer_stage_elems);
 size_t slab_link_stage_elems(const Sim* s);
 int launch_slab_exchange(Sim* s, int field_mask);
 int launch_slab_exchange_on(Sim* s, int field_mask, cudaStream_t stream);
+int launch_slab_range_reduce(Sim* s, cudaStream_t stream);  // d_range[0..1] of every slab -> d_range[2..3] everywhere
+int launch_slab_push_wait(Sim* s, int passes, int signature);              // the neighbours' pushes of a step's last pass have landed
+struct LinkInfo;                                             // what neighbours trade once (sayal_slab_ipc_export)
+int slab_link_export(Sim* s, LinkInfo* out);
+int slab_link_connect_info(Sim* s, int side, const LinkInfo* info, void* peer_block, void* peer_vel);
 
 // ---- visual.cu -------------------------------------------------------------------------------------
 int launch_diffusion(Sim* s, int iterations, float d_t);
@@ -185,7 +265,8 @@ int launch_arrows(Sim* s, const sayal_visual* v, int nx, int ny, sayal_arrow* d_
 int launch_projection_tiled(Sim* s, int iterations, float d_t);
 int tiled_max_temporal_block();
 int tiled_debug_pass_plans(int pitch, int local_rows, int own_lo, int own_hi, int rows_per_warp, int T, int iterations,
-                           int ghost_depth, int32_t* out, int capacity);  // host only; 11 int32 per pass, see sayal.h
+                           int ghost_depth, int32_t* out, int capacity);  // host only; 15 int32 per pass, see sayal.h
+int tiled_push_temporal_block(int iterations, int halo);  // push mode: the T every rank of a chain uses
 int tiled_preload();  // load every kernel variant now (never lazily in the middle of a linked step)
 int tiled_prepare(Sim* s, int iterations);  // choose the tile plan (may time candidates; not capturable)
 int tiled_prepare_windows(Sim* s, int iterations, int ghost_depth);  // + the issue orders of a linked slab's row windows

@@ -209,7 +209,7 @@ int launch_diffusion(Sim* s, int iterations, float d_t) {
 int launch_render_pixels(Sim* s, uint32_t* d_pixels) {
   dim3 block(64, 4);
   dim3 grid(((s->g.W + 3) / 4 + block.x - 1) / block.x, (s->g.own_hi - s->g.own_lo + block.y - 1) / block.y);
-  render_pixels_kernel<<<grid, block, 0, s->stream>>>(s->g, s->flags, s->smoke, s->p, s->d_range, s->ph.enable_pressure,
+  render_pixels_kernel<<<grid, block, 0, s->stream>>>(s->g, s->flags, s->smoke, s->p, s->d_range + (is_linked(s) ? 2 : 0), s->ph.enable_pressure,
                                                      s->ph.enable_smoke, d_pixels);
   VIS_LAUNCH_CHECK(s, "render_pixels_kernel");
   return SAYAL_OK;

@@ -74,8 +74,9 @@ class Config:
         self.c = c
 
     @classmethod
-    def defaults(cls, width: int = 1920, height: int = 1080, **overrides) -> "Config":
-        cfg = cls(width=width, height=height)
+    def defaults(cls, width: int = 1920, height: int = 1080, _struct=None, **overrides) -> "Config":
+        """_struct: a ready-made SayalConfig to start from instead of asking the library for the defaults."""
+        cfg = cls(_struct(width, height), width, height) if _struct is not None else cls(width=width, height=height)
         for key, value in overrides.items():
             cfg[key] = value
         return cfg
@@ -355,6 +356,40 @@ class Fluid:
         """Measurement aid: hold the sim's stream so that a timed region can be enqueued ahead of the device."""
         check(self._lib.sayal_stream_delay(self._sim, int(microseconds)))
 
+    def stream_hold(self) -> None:
+        """Everything enqueued after this call waits on the device until stream_release()."""
+        check(self._lib.sayal_stream_hold(self._sim))
+
+    def stream_release(self) -> None:
+        check(self._lib.sayal_stream_release(self._sim))
+
+    def plan_log(self) -> str:
+        """The tile plans the tuner considered for the last projection it planned (marked: the chosen one)."""
+        buf = C.create_string_buffer(4096)
+        check(min(self._lib.sayal_plan_log(self._sim, buf, 4096), 0))
+        return buf.value.decode()
+
+    def set_field_device(self, name: str, dev_ptr: int) -> None:
+        """Owned rows from a device buffer in the reference layout (row pitch W); asynchronous on the sim's stream."""
+        check(self._lib.sayal_set_field_device(self._sim, _abi.FIELD_NAMES[name], C.c_void_p(dev_ptr)))
+
+    def get_field_device(self, name: str, dev_ptr: int) -> None:
+        check(self._lib.sayal_get_field_device(self._sim, _abi.FIELD_NAMES[name], C.c_void_p(dev_ptr)))
+
+    def set_fields_from(self, pointers: dict) -> None:
+        """sayal_set_fields: {name: host address} — asynchronous for pinned memory (keep the buffers until sync)."""
+        n = len(pointers)
+        ids = (C.c_int32 * n)(*[_abi.FIELD_NAMES[k] for k in pointers])
+        ptrs = (C.c_void_p * n)(*[int(v) for v in pointers.values()])
+        check(self._lib.sayal_set_fields(self._sim, n, ids, ptrs))
+
+    def get_fields_into(self, pointers: dict) -> None:
+        """sayal_get_fields: {name: host address}; returns when every copy has landed."""
+        n = len(pointers)
+        ids = (C.c_int32 * n)(*[_abi.FIELD_NAMES[k] for k in pointers])
+        ptrs = (C.c_void_p * n)(*[int(v) for v in pointers.values()])
+        check(self._lib.sayal_get_fields(self._sim, n, ids, ptrs))
+
     @property
     def launch_count(self) -> int:
         return self._lib.sayal_launch_count(self._sim)
@@ -364,14 +399,15 @@ class Fluid:
         return self._lib.sayal_stream(self._sim) or 0
 
     # slab links (NVLink peer memory; see slab.py and csrc/slab_exchange.cu)
-    def ipc_export(self) -> Tuple[bytes, int]:
-        buf = C.create_string_buffer(64)
-        n = C.c_int64()
-        check(self._lib.sayal_slab_ipc_export(self._sim, buf, C.byref(n)))
-        return buf.raw, n.value
+    def ipc_export(self) -> bytes:
+        """The opaque blob a neighbouring rank needs to reach this slab (IPC handles + geometry)."""
+        buf = C.create_string_buffer(_abi.LINK_INFO_BYTES)
+        check(self._lib.sayal_slab_ipc_export(self._sim, buf))
+        return buf.raw
 
-    def ipc_connect(self, side: int, handle: bytes, stage_elems: int) -> None:
-        check(self._lib.sayal_slab_ipc_connect(self._sim, side, C.c_char_p(handle), stage_elems))
+    def ipc_connect(self, side: int, info: bytes) -> None:
+        buf = C.create_string_buffer(info, _abi.LINK_INFO_BYTES)
+        check(self._lib.sayal_slab_ipc_connect(self._sim, side, buf))
 
     def connect_local(self, side: int, neighbour: "Fluid") -> None:
         check(self._lib.sayal_slab_connect_local(self._sim, side, neighbour._sim))

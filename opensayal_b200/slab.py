@@ -12,7 +12,7 @@ Why ghost rows are enough (and keep the result bit-identical to one GPU):
     kernels count every sample that would leave them (`halo_overflow`); a non-zero count is an error.
   * forces / extrapolation are functions of position and of the local neighbour row: applied to every held row.
 
-Two schedules, both bit-identical to one GPU:
+Three schedules, all bit-identical to one GPU:
   * `step_schedule` (driven from Python, NCCL / gloo / device-copy exchanges): forces, [projection chunk,
     exchange(u,v)] x ceil(n / (halo/2)), extrapolation, velocity advection, exchange(u,v), smoke advection,
     exchange(smoke).
@@ -20,6 +20,11 @@ Two schedules, both bit-identical to one GPU:
     peer-memory stores over NVLink from its own kernels, the whole step one CUDA-graph replay): exchanges only when
     the remaining ghost depth is too small for the next operation, plus one exchange of u, v, smoke at the end of
     the step — ONE exchange per step when halo >= 2 n + margin + 1, hidden behind the interior smoke advection.
+
+  * `push_schedule` (the library's default for linked slabs, csrc/projection_pack.cu): every projection pass of
+    `it` iterations sweeps the owned rows +- 2 it, writes the owned rows, and its edge tiles store the new edge rows
+    straight into the neighbours' ghost rows — as data: [projection(it, depth 2 it), exchange(u, v)] per pass.  Ghost
+    rows cost 2 T + margin instead of 2 n + margin; compute and exchange are one kernel.
 
 The schedule is data (a list of ops), so the same program drives real slabs over torch.distributed, several
 slabs on one GPU (tests) and a numpy stand-in under gloo on CPU (tests of the host logic).
@@ -39,14 +44,31 @@ def slab_rows(height: int, world: int, rank: int) -> Tuple[int, int]:
     return row0, rows
 
 
-def step_schedule(n_iterations: int, halo: int, pressure: bool, smoke: bool) -> List[tuple]:
-    """One Fluid::update (fluid.cu:770-795) as slab operations."""
+def _diffusion_ops(n_iterations: int, halo: int) -> List[tuple]:
+    """apply_diffusion (fluid.cu:775-777): n sweeps over u when fluid.viscosity != 0.  A sweep reaches one row per
+    colour like a projection half-sweep, so it is chunked the same way: halo // 2 sweeps, then an exchange of u —
+    what step_impl (csrc/sayal_api.cu) does for linked slabs."""
+    ops: List[tuple] = []
+    per, done = halo // 2, 0
+    while done < n_iterations:
+        k = min(per, n_iterations - done)
+        ops.append(("diffusion", k))
+        ops.append(("exchange", F_U))
+        done += k
+    return ops
+
+
+def step_schedule(n_iterations: int, halo: int, pressure: bool, smoke: bool, viscous: bool = False) -> List[tuple]:
+    """One Fluid::update (fluid.cu:770-795) as slab operations.  viscous: fluid.viscosity != 0 (the reference's
+    shipped default is 0.001, config_parser.cpp:117)."""
     if halo < 2:
         raise ValueError("halo must be >= 2 rows (one SOR iteration reaches two rows)")
     per = halo // 2
     ops: List[tuple] = [("forces",)]
     if pressure:
         ops.append(("zero_pressure",))
+    if viscous:
+        ops += _diffusion_ops(n_iterations, halo)
     done = 0
     while done < n_iterations:
         k = min(per, n_iterations - done)
@@ -106,6 +128,47 @@ def lazy_schedule(n_iterations: int, halo: int, pressure: bool, smoke: bool, mar
     return ops
 
 
+def push_temporal_block(n_iterations: int, halo: int) -> int:
+    """The iterations per pass every rank of a chain uses in push mode (tiled_push_temporal_block, projection_pack.cu):
+    the even split of n into passes of at most min(halo // 2, 8)."""
+    cap = min(halo // 2, 8)
+    if cap < 1 or n_iterations <= 0:
+        return 0
+    passes = -(-n_iterations // cap)
+    return -(-n_iterations // passes)
+
+
+def push_schedule(n_iterations: int, halo: int, pressure: bool, smoke: bool, margin: int = 16,
+                  temporal_block: Optional[int] = None, viscous: bool = False) -> List[tuple]:
+    """The library's default schedule for linked slabs (push mode), as data.  Pass k of `it` iterations sweeps the
+    owned rows +- 2 it ghost rows (("projection", it, 2 it): the shrinking window of that pass) and its edge tiles
+    deliver the new edge rows to the neighbours, which the stand-in expresses as an exchange of u and v after the
+    pass.  Needs halo >= max(2 T, margin + 1)."""
+    T = temporal_block or push_temporal_block(n_iterations, halo)
+    if halo < margin + 1 or (n_iterations > 0 and (T < 1 or 2 * T > halo)):
+        raise ValueError("push mode needs halo >= max(2 T, margin + 1)")
+    ops: List[tuple] = [("forces",)]
+    if pressure:
+        ops.append(("zero_pressure",))
+    if viscous:
+        ops += _diffusion_ops(n_iterations, halo)
+    if n_iterations > 0:
+        passes = -(-n_iterations // T)
+        base, longer = divmod(n_iterations, passes)
+        for k in range(passes):
+            it = base + (1 if k < longer else 0)
+            ops.append(("projection", it, 2 * it))
+            ops.append(("exchange", F_U | F_V))
+    if pressure:
+        ops.append(("pressure_range",))
+    ops.append(("extrapolation",))
+    ops.append(("advect_velocity", 1))
+    if smoke:
+        ops.append(("advect_smoke",))
+    ops.append(("exchange", F_U | F_V | (F_SMOKE if smoke else 0)))
+    return ops
+
+
 def n_fields(mask: int) -> int:
     return bin(mask & 0xF).count("1")
 
@@ -140,6 +203,8 @@ class FluidSlab:
             s.stage_zero_pressure()
         elif kind == "projection":
             s.stage_projection(op[1], d_t)
+        elif kind == "diffusion":
+            s.stage_diffusion(op[1], d_t)
         elif kind == "pressure_range":
             pass  # stage_projection already queued the local range; the global one is an all-reduce (pressure_range())
         elif kind == "extrapolation":
@@ -253,9 +318,9 @@ def link_dist(sim, rank: int, world: int, group=None) -> None:
     everyone = [None] * world
     dist.all_gather_object(everyone, mine, group=group)
     if rank > 0:
-        sim.ipc_connect(0, *everyone[rank - 1])
+        sim.ipc_connect(0, everyone[rank - 1])
     if rank < world - 1:
-        sim.ipc_connect(1, *everyone[rank + 1])
+        sim.ipc_connect(1, everyone[rank + 1])
     dist.barrier(group=group)
 
 
@@ -266,18 +331,20 @@ class SlabFluid:
     kernels on the sim's stream (csrc/slab_exchange.cu) and the whole step is one CUDA-graph replay per rank.
     transport "nccl": the same schedule driven from here, edge rows packed and sent with NCCL send/recv."""
 
-    def __init__(self, cfg, rank: int, world: int, device: int, halo: int = 16, group=None, transport: str = "p2p",
-                 margin: int = 16):
+    def __init__(self, cfg, rank: int, world: int, device: int, halo: Optional[int] = None, group=None,
+                 transport: str = "p2p", margin: int = 16):
         self.cfg, self.rank, self.world, self.group = cfg, rank, world, group
         self.transport = transport if world > 1 else "none"
         c = cfg.c
+        if halo is None:  # enough for a step in push mode: 2 T <= 16 rows per pass, margin + 2 rows for the advection
+            halo = max(margin + 2, 16)
         row0, rows = slab_rows(c.height, world, rank)
         if world > 1 and rows < halo:
             raise ValueError(f"slab of {rows} rows is thinner than the halo ({halo})")
         self.row0, self.rows, self.halo = row0, rows, halo
         self.slab = FluidSlab(cfg, device, row0, rows, halo if world > 1 else 0, rank == 0, rank == world - 1)
-        self.ops = step_schedule(c.proj_n, halo, bool(c.enable_pressure), bool(c.enable_smoke) and c.wt_smoke != 0) \
-            if world > 1 else None
+        self.ops = step_schedule(c.proj_n, halo, bool(c.enable_pressure), bool(c.enable_smoke) and c.wt_smoke != 0,
+                                 viscous=c.viscosity != 0) if world > 1 else None
         if self.transport == "p2p":
             self.sim.set_option("advect_margin", margin)  # rows the advection may gather from (see lazy_schedule)
             link_dist(self.sim, rank, world, group)
@@ -318,11 +385,13 @@ class SlabFluid:
         return self.sim.get_option("halo_overflow")
 
     def pressure_range(self):
+        """Fluid::min_pressure / max_pressure of the whole domain.  Linked slabs get it from the library (reduced along
+        the chain inside the step); the NCCL transport all-reduces the per-slab pairs here."""
+        mn, mx = self.sim.min_pressure, self.sim.max_pressure
+        if self.world == 1 or self.transport == "p2p":
+            return mn, mx
         import torch
         import torch.distributed as dist
-        mn, mx = self.sim.min_pressure, self.sim.max_pressure
-        if self.world == 1:
-            return mn, mx
         t = torch.tensor([mn, -mx], dtype=torch.float32, device=self.slab.device)
         dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
         return float(t[0]), float(-t[1])
@@ -332,9 +401,164 @@ class SlabFluid:
 
 
 # ----------------------------------------------------------------------------------------------------
+GATED_CHUNK = 40  # steps enqueued behind one gate: stays far below the driver's launch-queue depth
+
+
+def gated_steps(sim, steps, one_step, events, barrier):
+    """Run `steps` timed steps so that no host work can fall inside the timed region: per chunk, hold the stream with
+    the host-released gate, enqueue two untimed alignment steps and the chunk's timed steps, meet the other ranks at a
+    HOST barrier (every rank has enqueued everything), then open the gate.  The device then runs the whole chunk from
+    its queue; a host thread that stalls afterwards cannot make a neighbour wait for rows."""
+    done = 0
+    while done < steps:
+        n = min(GATED_CHUNK, steps - done)
+        sim.stream_hold()
+        one_step()
+        one_step()
+        for k in range(done, done + n):
+            one_step(*events[k])
+        barrier()
+        sim.stream_release()
+        sim.sync()
+        done += n
+
+
+def device_fields(width, height, rows, device):
+    """Synthetic u, v, smoke of memory rows [r0, r0 + n) generated on the GPU (torch), for grids where the numpy
+    generator of synthetic.py would take longer than the measurement (16384 x 16384).  Same modes, no noise term."""
+    import math
+
+    import torch
+    r0, n = rows
+    r = torch.arange(r0, r0 + n, dtype=torch.float64, device=device)[:, None]
+    y = (height - 1 - r) + 0.5
+    x = torch.arange(width, dtype=torch.float64, device=device)[None, :] + 0.5
+    two_pi = 2.0 * math.pi
+    cx, sx = torch.cos(two_pi * 3 * x / width), torch.sin(two_pi * 3 * x / width)
+    u = (40.0 * sx * torch.cos(two_pi * 2 * y / height)).float()
+    v = (-40.0 * cx * torch.sin(two_pi * 2 * y / height)).float()
+    smoke = (0.5 * (1.0 + torch.sin(two_pi * 8 * x / width) * torch.sin(two_pi * 8 * y / height))).float()
+    return u.contiguous(), v.contiguous(), smoke.contiguous()
+
+
+def strong_16384_record(world, rank, local, steps=8, width=16384, height=16384, iters=50, with_single=True):
+    """BASELINE configs[3]: 16384 x 16384, n = 50, strong scaling over `world` y-slabs (north_star: >= 85 % parallel
+    efficiency at 8 GPUs).  Returns, on rank 0, {"ms_per_step": ..., "n1_ms_per_step": ...}: the time of the N-slab
+    run and — measured in the same process on rank 0's GPU after the slabs are gone — of the single-GPU run."""
+    import torch
+    import torch.distributed as dist
+
+    from .fluid import Fluid
+    from .synthetic import baseline_config
+
+    def config():
+        cfg = baseline_config(3, width=width, height=height)
+        cfg["sim.projection.n"] = iters
+        return cfg
+
+    def timed(sim_like, sim, barrier):
+        stream = torch.cuda.ExternalStream(sim.stream)
+        sim_like.run(3)
+        sim_like.sync()
+        events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+
+        def one_step(a=None, b=None):
+            if a is not None:
+                a.record(stream)
+            sim_like.run(1)
+            if b is not None:
+                b.record(stream)
+
+        gated_steps(sim, steps, one_step, events, barrier)
+        return sum(a.elapsed_time(b) for a, b in events) / steps
+
+    def load(sim, row0, rows):
+        u, v, sm = device_fields(width, height, (row0, rows), torch.device("cuda", local))
+        torch.cuda.current_stream().synchronize()
+        for name, t in (("u", u), ("v", v), ("smoke", sm)):
+            sim.set_field_device(name, t.data_ptr())
+        sim.sync()  # the tensors may go once the copies are done
+
+    out = {"grid": [width, height], "sor_iterations": iters, "steps": steps, "scaling": "strong", "n_gpus": world}
+    if world > 1:
+        sf = SlabFluid(config(), rank, world, local)
+        load(sf.sim, sf.row0, sf.rows)
+        sf.sim.slab_exchange(F_U | F_V | F_SMOKE)
+        ms = timed(sf, sf.sim, dist.barrier)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        bad = torch.tensor([sf.halo_overflow(), sf.sim.get_option("link_error")], dtype=torch.int64, device="cuda")
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        out.update(ms_per_step=float(t[0]), halo_rows=sf.halo, halo_overflow=int(bad[0]), link_error=int(bad[1]),
+                   push_mode=bool(sf.sim.get_option("push_mode")),
+                   plan=[sf.sim.get_option("plan_temporal_block"), sf.sim.get_option("plan_rows_per_warp")])
+        sf.close()
+        dist.barrier()
+    if rank == 0 and (with_single or world == 1):
+        f = Fluid(config(), device=local)
+        load(f, 0, height)
+        ms1 = timed(f, f, lambda: None)
+        out["n1_ms_per_step"] = ms1
+        out["n1_plan"] = [f.get_option("plan_temporal_block"), f.get_option("plan_rows_per_warp")]
+        if world == 1:
+            out["ms_per_step"] = ms1
+        f.close()
+    if world > 1:
+        dist.barrier()
+    if "ms_per_step" in out:
+        out["cell_steps_per_s"] = width * height / (out["ms_per_step"] * 1e-3)
+    if world > 1 and "n1_ms_per_step" in out:
+        out["speedup_vs_1gpu_same_box"] = out["n1_ms_per_step"] / out["ms_per_step"]
+    return out if rank == 0 else None
+
+
+def slab_parity_vs_single(cfg, sf, rank, world, local, steps=3):
+    """The multi-GPU test proper, inside the bench (the GPU test box has one GPU): restart the slabs from the synthetic
+    fields, run `steps` updates, gather the owned rows on rank 0 and compare them BIT FOR BIT with the same domain
+    stepped on one GPU.  Returns a dict on rank 0."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from .fluid import Fluid
+    from .synthetic import synthetic_fields
+
+    c = cfg.c
+    u, v, sm = synthetic_fields(c.width, c.height, rows=(sf.row0, sf.rows))
+    sf.set_initial(u, v, sm)
+    sf.run(steps)
+    sf.sync()
+    names = ("u", "v", "smoke")
+    mine = {n: sf.sim.get_field(n) for n in names}
+    status = (sf.halo_overflow(), sf.sim.get_option("link_error"))
+    parts = [None] * world
+    dist.gather_object((mine, status), parts if rank == 0 else None, dst=0)
+    result = None
+    if rank == 0:
+        f = Fluid(cfg, device=local)
+        gu, gv, gs = synthetic_fields(c.width, c.height)
+        for n, a in (("u", gu), ("v", gv), ("smoke", gs)):
+            f.set_field(n, a)
+        f.run(steps)
+        f.sync()
+        mismatched = {}
+        for n in names:
+            got = np.concatenate([p[0][n] for p in parts])
+            want = f.get_field(n)
+            # bit-for-bit (NaN-safe): compare the words, not the values
+            mismatched[n] = int((got.view(np.uint32) != want.view(np.uint32)).sum())
+        f.close()
+        result = {"steps": steps, "fields": list(names), "mismatched_cells": mismatched,
+                  "bit_identical": all(m == 0 for m in mismatched.values()),
+                  "halo_overflow": int(sum(p[1][0] for p in parts)), "link_error": int(max(p[1][1] for p in parts))}
+    dist.barrier()
+    return result
+
+
 def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSampler, measured_hbm_peak: Callable,
                 algorithmic_bytes_per_cell_step: Callable):
     """bench.py's N > 1 leg: weak scaling, one rank per GPU, launched by torch.distributed.run."""
+    import gc
     import os
     import time
 
@@ -361,12 +585,11 @@ def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSa
     cfg = workload_config(world)
     c = cfg.c
     margin = int(os.environ.get("SAYAL_ADVECT_MARGIN", "16"))
-    # deep halo: 2 n + margin + 1 ghost rows keep the owned rows exact through a whole step, so the step needs ONE
-    # exchange (hidden behind the interior smoke advection); thin slabs fall back to exchanging every halo/2 iterations
-    rows_per_rank = c.height // world
-    halo = int(os.environ.get("SAYAL_SLAB_HALO", "0")) or min(2 * c.proj_n + margin + 2, max(margin + 2, rows_per_rank // 4))
+    # push mode (default): 2 T + margin ghost rows are enough, the projection passes deliver their own edge rows;
+    # SAYAL_SLAB_PUSH=0 + SAYAL_SLAB_HALO=118 measures the deep-halo schedule of round 1
+    halo = int(os.environ.get("SAYAL_SLAB_HALO", "0")) or max(margin + 2, 16)
     transport = os.environ.get("SAYAL_SLAB_TRANSPORT", "p2p")
-    sf = SlabFluid(cfg, rank, world, local, halo=halo, transport=transport)
+    sf = SlabFluid(cfg, rank, world, local, halo=halo, transport=transport, margin=margin)
     u, v, sm = synthetic_fields(c.width, c.height, rows=(sf.row0, sf.rows))
     sf.set_initial(u, v, sm)
     stream = sf.slab.stream
@@ -390,30 +613,18 @@ def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSa
     sf.sync()
     dist.barrier()
     torch.cuda.synchronize()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    # Two untimed steps after the barrier: ranks leave a barrier up to ~0.1 ms apart, and the neighbours of a late
-    # rank would book that wait into their first timed steps.  The exchanges of these two steps line the ranks
-    # up on the device; the K timed steps follow back to back in the same queue.
-    import gc
+    events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     gc.collect()
     gc.disable()  # no collector pause in the enqueue loop
-    with ClockSampler(local, period=0.004) as clocks:  # started before the untimed steps: its first query is slow
-        # Hold the stream while the host enqueues the whole region (about 0.15 ms of host time per step): a rank whose
-        # host thread stalls for a few milliseconds would otherwise drain its queue, and its neighbours would book
-        # the wait for its rows as a slow step (seen at 8 ranks: one 3.5 ms step in fifty).
-        sf.sim.stream_delay(min(200000, 2000 + 400 * args.steps))
-        one_step()
-        one_step()
-        launches0 = sf.sim.launch_count
-        for k in range(args.steps):
-            one_step(starts[k], stops[k])
-        sf.sync()
+    launches0 = sf.sim.launch_count
+    with ClockSampler(local, period=0.004) as clocks:
+        gated_steps(sf.sim, args.steps, one_step, events, dist.barrier)
         torch.cuda.synchronize()
         dist.barrier()
     gc.enable()
-    launches = sf.sim.launch_count - launches0
-    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    untimed = 2 * -(-args.steps // GATED_CHUNK)  # alignment steps
+    launches = (sf.sim.launch_count - launches0) * args.steps // (args.steps + untimed)
+    step_ms = [s.elapsed_time(e) for s, e in events]
     ms_local = sum(step_ms) / args.steps
     mine = torch.tensor(step_ms, dtype=torch.float64, device="cuda")
     every = [torch.zeros_like(mine) for _ in range(world)]
@@ -422,32 +633,35 @@ def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSa
     worst = every.max(dim=0).values           # slowest rank of every step
     per_step = sorted(float(x) for x in worst)
     k_bad = int(worst.argmax())
-    med = per_step[len(per_step) // 2]
     slowest_step = {"index": k_bad, "ms": round(float(worst[k_bad]), 4),
                     "ms_per_rank": [round(float(x), 3) for x in every[:, k_bad]]}
     if os.environ.get("SAYAL_BENCH_DEBUG"):
         import sys
-        gaps = [stops[k].elapsed_time(starts[k + 1]) for k in range(args.steps - 1)]
         print(f"[rank {rank}] step ms: min {min(step_ms):.4f} med {sorted(step_ms)[len(step_ms) // 2]:.4f} max {max(step_ms):.4f}; "
-              f"flush gap ms: med {sorted(gaps)[len(gaps) // 2]:.4f} max {max(gaps):.4f}; first 8: {[round(x, 3) for x in step_ms[:8]]}",
-              file=sys.stderr, flush=True)
+              f"first 8: {[round(x, 3) for x in step_ms[:8]]}", file=sys.stderr, flush=True)
     t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
-    overflow = torch.tensor([sf.halo_overflow()], dtype=torch.int64, device="cuda")
-    dist.all_reduce(overflow, op=dist.ReduceOp.SUM)
+    bad = torch.tensor([sf.halo_overflow(), sf.sim.get_option("link_error")], dtype=torch.int64, device="cuda")
+    dist.all_reduce(bad, op=dist.ReduceOp.MAX)
     cells = c.width * c.height
     value = cells / (ms * 1e-3)
 
-    # end to end: owned rows from pinned host buffers, K steps, owned rows back — wall clock, max over ranks
+    # end to end: owned rows from pinned host buffers (one batched upload), K steps, owned rows back (one batched
+    # download) — wall clock, max over ranks
     pinned = {k: torch.from_numpy(a).pin_memory() for k, a in (("u", u), ("v", v), ("smoke", sm))}
+    outs = {k: torch.empty_like(t_).pin_memory() for k, t_ in pinned.items()}
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    sf.set_initial(pinned["u"].numpy(), pinned["v"].numpy(), pinned["smoke"].numpy())
+    sf.sim.set_fields_from({k: t_.data_ptr() for k, t_ in pinned.items()})
+    if transport == "p2p":
+        sf.sim.slab_exchange(F_U | F_V | F_SMOKE)
+    else:
+        exchange_dist(sf.slab, F_U | F_V | F_SMOKE, rank, world, None)
     for _ in range(args.steps):
         sf.update()
-    outs = [sf.sim.get_field(n) for n in ("u", "v", "smoke")]
+    sf.sim.get_fields_into({k: t_.data_ptr() for k, t_ in outs.items()})
     t1 = time.perf_counter()
     te = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
     dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -456,9 +670,20 @@ def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSa
     launches_t = torch.tensor([launches], dtype=torch.int64, device="cuda")
     dist.all_reduce(launches_t, op=dist.ReduceOp.SUM)
     plan_t = torch.tensor([sf.sim.get_option("plan_temporal_block"), sf.sim.get_option("plan_rows_per_warp"),
-                           sf.sim.get_option("local_rows")], dtype=torch.int64, device="cuda")
+                           sf.sim.get_option("local_rows"), sf.sim.get_option("push_mode")], dtype=torch.int64, device="cuda")
     plans = [torch.zeros_like(plan_t) for _ in range(world)]
     dist.all_gather(plans, plan_t)
+
+    # N slabs == one GPU, bit for bit (rank 0 steps the stacked domain on its own GPU and compares)
+    parity = None if os.environ.get("SAYAL_BENCH_SKIP_PARITY") else slab_parity_vs_single(cfg, sf, rank, world, local)
+    sf.close()
+    del flush
+    torch.cuda.empty_cache()
+    dist.barrier()
+    strong = None
+    if not os.environ.get("SAYAL_BENCH_SKIP_STRONG"):
+        strong = strong_16384_record(world, rank, local)
+
     peak, peak_src = measured_hbm_peak()
     b_alg = algorithmic_bytes_per_cell_step(c.proj_n, int(bool(c.enable_pressure)), 1)
     line = None
@@ -467,11 +692,16 @@ def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSa
             "metric": "cell-steps/sec (n=50 SOR)", "value": value, "unit": "cell-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_block(cfg, world, {"halo_rows": halo, "exchange": "peer-memory stores over NVLink from the library's kernels, graph-replayed step" if transport == "p2p"
-                                                else "NCCL send/recv of packed edge rows",
-                                                "halo_overflow": int(overflow[0]),
-                                                "tile_plans_per_rank": [{"temporal_block": int(p[0]), "rows_per_warp": int(p[1]),
-                                                                         "local_rows": int(p[2])} for p in plans]}),
+            "config": config_block(cfg, world),
+            "slabs": {"halo_rows": halo, "push_mode": bool(int(plans[0][3])),
+                      "exchange": ("projection passes store their edge rows into the neighbour's ghost rows over NVLink (one kernel "
+                                   "computes and exchanges); end-of-step exchange kernel under the smoke advection; graph-replayed step")
+                      if transport == "p2p" else "NCCL send/recv of packed edge rows",
+                      "halo_overflow": int(bad[0]), "link_error": int(bad[1]),
+                      "tile_plans_per_rank": [{"temporal_block": int(p[0]), "rows_per_warp": int(p[1]),
+                                               "local_rows": int(p[2])} for p in plans]},
+            "timing": "all ranks enqueue 2 alignment + K timed steps behind a host-released gate, meet at a host barrier, "
+                      "then open the gate; CUDA events per step on every rank's stream, mean over steps, max over ranks",
             "roofline": {"bound": "hbm", "kernel": "whole step, all GPUs", "achieved": round(value * b_alg / 1e9, 1),
                          "peak": peak * world, "unit": "GB/s", "frac": round(value * b_alg / 1e9 / (peak * world), 4),
                          "traffic": None, "peak_source": peak_src + f" x {world} GPUs"},
@@ -482,8 +712,14 @@ def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSa
             "step_ms_slowest_rank": {"min": round(per_step[0], 4), "median": round(per_step[len(per_step) // 2], 4),
                                      "p90": round(per_step[int(0.9 * (len(per_step) - 1))], 4), "max": round(per_step[-1], 4),
                                      "slowest_step": slowest_step},
+            "parity_vs_single_gpu": parity, "link_error": int(bad[1]),
+            "strong_16384": strong,
         }
-    sf.close()
     dist.barrier()
     dist.destroy_process_group()
+    if rank == 0 and ((parity is not None and not parity["bit_identical"]) or int(bad[1]) or int(bad[0])):
+        import json
+        import sys
+        print(json.dumps(line), flush=True)
+        sys.exit(3)  # a throughput number over wrong fields is not a result
     return line

@@ -49,10 +49,14 @@ def synthetic_fields(width: int, height: int, seed: int = 1234, amplitude: float
     return u.astype(np.float32), v.astype(np.float32), smoke.astype(np.float32)
 
 
-def baseline_config(index: int, width: int | None = None, height: int | None = None) -> Config:
+def baseline_config(index: int, width: int | None = None, height: int | None = None, defaults=None) -> Config:
     """BASELINE.json `configs[index]` restated as concrete inputs.  All of them:
-    cell_size 1, density 1, drag 0, viscosity 0 (H1), o 1.9, d_t 0.05, inactive source."""
+    cell_size 1, density 1, drag 0, viscosity 0 (H1), o 1.9, d_t 0.05, inactive source.
+    defaults: callable (width, height) -> SayalConfig replacing the library's sayal_config_defaults (the reference
+    arm of bench.py passes oracle.reference_defaults so that it never maps the product library)."""
     common = {"fluid.viscosity": 0.0, "fluid.drag_coeff": 0.0, "sim.projection.o": 1.9, "sim.time.d_t": 0.05}
+    if defaults is not None:
+        common["_struct"] = defaults
     if index == 0:  # 256x144 gravity tank
         w, h = width or 256, height or 144
         return Config.defaults(w, h, **common, **{

@@ -17,6 +17,25 @@ ORACLE_LIB = HERE / "liboracle.so"
 REF_LIB = HERE / "_ref" / "libsayal_ref.so"
 
 
+def reference_defaults(width: int = 1920, height: int = 1080) -> SayalConfig:
+    """The defaults of the reference's ConfigParser::parse (/root/reference/src/config_parser.cpp:21-119) restated
+    in Python, so that the reference arm of bench.py can build its configuration without mapping the product library
+    (sayal_config_defaults).  tests/test_config.py checks that the two agree."""
+    c = SayalConfig()
+    c.width, c.height, c.cell_size = width, height, 1.0
+    c.enable_drain, c.enable_pressure, c.enable_smoke, c.enable_interactive = 1, 0, 1, 0
+    c.proj_n, c.proj_o = 50, 1.9
+    c.wt_pipe_height, c.wt_pipe_length, c.wt_smoke_length = height // 4, 0, 1
+    c.wt_smoke_height, c.wt_smoke_count, c.wt_speed, c.wt_smoke = height // 4, 1, 0.0, 1.0
+    c.g, c.d_t, c.enable_real_time, c.real_time_multiplier = 0.0, 0.05, 0, 1.0
+    c.smoke_enable_decay, c.smoke_decay_rate = 0, 0.05
+    c.obstacle_enable, c.obstacle_center_x, c.obstacle_center_y = 1, width // 2, height // 2
+    c.obstacle_radius = min(height, width) / 30.0
+    c.density, c.drag_coeff, c.viscosity = 1.0, 0.0, 0.001
+    c.block_size_x, c.block_size_y = 64, 1
+    return c
+
+
 def build(ref: bool = True) -> None:
     subprocess.run(["make", "-C", str(HERE), "liboracle.so"] + (["ref"] if ref else []), check=True,
                    capture_output=True, text=True)

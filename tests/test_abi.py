@@ -27,7 +27,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_load_and_version():
     lib = load()
-    assert lib.sayal_abi_version() == 2
+    assert lib.sayal_abi_version() == 3
     assert lib.sayal_last_error() is not None
 
 
@@ -47,3 +47,16 @@ def test_no_oracle_in_product():
             continue
         text = path.read_text(errors="ignore")
         assert "liboracle" not in text and "from oracle" not in text and "import oracle" not in text, path
+
+
+def test_host_only_entry_points_do_not_need_a_gpu():
+    """Argument checks and host-side helpers answer without a device (no compute call here)."""
+    import ctypes as C
+    lib = load()
+    assert lib.sayal_stream_hold(None) < 0 and lib.sayal_stream_release(None) < 0
+    assert lib.sayal_get_fields(None, 0, None, None) < 0 and lib.sayal_set_fields(None, 0, None, None) < 0
+    assert lib.sayal_slab_ipc_export(None, None) < 0
+    assert lib.sayal_plan_log(None, None, 0) < 0
+    assert b"null" in lib.sayal_last_error()
+    from opensayal_b200 import _abi
+    assert _abi.LINK_INFO_BYTES == 256 and _abi.SAYAL_ELINK == -7

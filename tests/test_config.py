@@ -105,3 +105,20 @@ def test_config_views():
     cfg.sim.projection.n = 9
     assert cfg.c.proj_n == 9
     assert cfg.fluid.density == 1.0
+
+
+def test_python_restatement_of_the_defaults_matches_the_library():
+    """bench.py's reference arm builds its configuration from oracle.reference_defaults (so that it never maps the
+    product library); it must be the same struct, byte for byte, as sayal_config_defaults gives."""
+    import ctypes as C
+
+    from opensayal_b200 import load
+    from opensayal_b200._abi import SayalConfig
+    from opensayal_b200.synthetic import baseline_config
+    from oracle.oracle import reference_defaults
+    for w, h in ((1920, 1080), (256, 144), (101, 67), (16384, 16384), (3840, 2160)):
+        c = SayalConfig()
+        assert load().sayal_config_defaults(w, h, C.byref(c)) == 0
+        assert bytes(c) == bytes(reference_defaults(w, h)), (w, h)
+    for index in range(5):
+        assert bytes(baseline_config(index).c) == bytes(baseline_config(index, defaults=reference_defaults).c)

@@ -75,6 +75,20 @@ class NumpySlab:
                         assert self.lo <= src < self.hi, "back-trace left the ghost rows"
                         new[lr, i] = a[src - self.lo, i]
                 self.f[name] = new
+        elif kind == "diffusion":  # in-place sweeps over u with one-row reach per colour, like apply_diffusion
+            a = self.f["u"]
+            for m in range(op[1]):
+                for colour in (0, 1):
+                    new = a.copy()
+                    for lr in range(len(a)):
+                        r = self.lo + lr
+                        if r == 0 or r == H - 1 or (r + colour) % 2:
+                            continue
+                        up = a[lr - 1] if lr > 0 else 0.0
+                        dn = a[lr + 1] if lr + 1 < len(a) else 0.0
+                        new[lr] = (a[lr] + np.float32(0.125) * (up + dn)) / np.float32(1.25)
+                    a = new
+            self.f["u"] = a
         elif kind in ("extrapolation", "zero_pressure", "pressure_range"):
             pass
         else:
@@ -107,10 +121,10 @@ def initial():
     return {k: rng.standard_normal((H, W)).astype(np.float32) for k in ("u", "v", "smoke")}
 
 
-def single_domain(steps):
+def single_domain(steps, viscous=False):
     s = NumpySlab(initial(), 0, H, 0, True, True)
     ops = [op[:1] + op[1:] if op[0] != "advect_velocity" else ("advect_velocity",)
-           for op in S.step_schedule(N_ITER, 8, False, True) if op[0] != "exchange"]
+           for op in S.step_schedule(N_ITER, 8, False, True, viscous=viscous) if op[0] != "exchange"]
     for _ in range(steps):
         for op in ops:
             s.apply(op)
@@ -191,6 +205,61 @@ def test_shrinking_row_window_matches_single_domain(world, halo):
     for _ in range(3):
         S.run_schedule_local(slabs, ops)
     want = single_domain(3)
+    for s in slabs:
+        for name in ("u", "v", "smoke"):
+            assert np.array_equal(s.owned(name), want[name][s.row0:s.row0 + s.rows]), (name, s.row0)
+
+
+@pytest.mark.parametrize("world,halo,T", [(2, 6, None), (3, 8, None), (2, 18, None), (3, 14, 7), (4, 5, 2), (2, 4, 1)])
+def test_push_schedule_matches_single_domain(world, halo, T):
+    """Push mode (the library's default for linked slabs): a pass of `it` iterations sweeps the owned rows +- 2 it and
+    the edge tiles hand the new edge rows to the neighbours — as data, a windowed projection followed by an exchange."""
+    full = initial()
+    slabs = []
+    for r in range(world):
+        row0, rows = S.slab_rows(H, world, r)
+        slabs.append(NumpySlab(full, row0, rows, halo, r == 0, r == world - 1))
+    ops = S.push_schedule(N_ITER, halo, False, True, margin=REACH, temporal_block=T)
+    proj = [op for op in ops if op[0] == "projection"]
+    assert sum(op[1] for op in proj) == N_ITER and all(op[2] == 2 * op[1] <= halo for op in proj)
+    for _ in range(3):
+        S.run_schedule_local(slabs, ops)
+    want = single_domain(3)
+    for s in slabs:
+        for name in ("u", "v", "smoke"):
+            assert np.array_equal(s.owned(name), want[name][s.row0:s.row0 + s.rows]), (name, s.row0)
+
+
+def test_push_schedule_shape():
+    assert S.push_temporal_block(50, 18) == 8 and S.push_temporal_block(50, 16) == 8 and S.push_temporal_block(50, 10) == 5
+    assert S.push_temporal_block(200, 18) == 8 and S.push_temporal_block(7, 18) == 7 and S.push_temporal_block(9, 18) == 5
+    ops = S.push_schedule(50, 18, False, True)
+    assert [op[1] for op in ops if op[0] == "projection"] == [8, 7, 7, 7, 7, 7, 7]
+    assert ops[-1] == ("exchange", S.F_U | S.F_V | S.F_SMOKE)
+    with pytest.raises(ValueError):
+        S.push_schedule(50, 18, False, True, temporal_block=10)  # 20 ghost rows per pass > 18
+    with pytest.raises(ValueError):
+        S.push_schedule(50, 12, False, True, margin=16)
+
+
+@pytest.mark.parametrize("schedule", ["step", "push"])
+def test_viscous_schedules_run_the_diffusion_stage(schedule):
+    """fluid.viscosity != 0 (the reference's shipped default): the slab schedules carry the diffusion sweeps with an
+    exchange of u every halo // 2 sweeps, like step_impl does; same result as the single domain."""
+    world, halo = 3, 6
+    full = initial()
+    slabs = []
+    for r in range(world):
+        row0, rows = S.slab_rows(H, world, r)
+        slabs.append(NumpySlab(full, row0, rows, halo, r == 0, r == world - 1))
+    ops = (S.step_schedule(N_ITER, halo, False, True, viscous=True) if schedule == "step"
+           else S.push_schedule(N_ITER, halo, False, True, margin=REACH, viscous=True))
+    assert sum(op[1] for op in ops if op[0] == "diffusion") == N_ITER
+    for _ in range(2):
+        S.run_schedule_local(slabs, ops)
+    want = single_domain(2, viscous=True)
+    plain = single_domain(2)
+    assert not np.array_equal(want["u"], plain["u"]), "the stand-in's diffusion must change u"
     for s in slabs:
         for name in ("u", "v", "smoke"):
             assert np.array_equal(s.owned(name), want[name][s.row0:s.row0 + s.rows]), (name, s.row0)
