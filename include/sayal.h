@@ -258,6 +258,9 @@ int sayal_plan_log(sayal_sim* sim, char* buf, int32_t capacity);
 /* Profiling only (option "debug_timeline" = 1): per-CTA timestamps of the last projection pass, 5 int64 per tile
  * {entry, tile loaded, sweeps done, stores issued (globaltimer ns), SM id}. */
 int sayal_debug_timeline(sayal_sim* sim, int64_t* host_dst, int32_t max_tiles, int32_t* n_tiles);
+/* Diagnostics of a slab link: the 64 neighbour-written control words of this sim followed by its 32 private counters
+ * (layout: csrc/sayal_internal.h), copied after the sim's stream has drained. */
+int sayal_debug_link_words(sayal_sim* sim, uint32_t* host_dst /* 96 words */);
 /* Measurement aid: hold the sim's stream for `microseconds` (<= 1e6) with a one-thread spin kernel, so that a whole
  * timed region can be enqueued before the device starts on it (host launch jitter then cannot drain the queue). */
 int sayal_stream_delay(sayal_sim* sim, int64_t microseconds);

@@ -449,4 +449,25 @@ int launch_pack_rows(Sim* s, int local_row0, int nrows, int field_mask, float* d
   return SAYAL_OK;
 }
 
+// Load this file's kernels now: CUDA loads a kernel lazily at its first launch, and that load can wait for the device
+// to drain — which never happens while a linked slab on the same device spins for rows this thread has yet to enqueue.
+int preload_basic() {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, forces_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, projection_half_sweep_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, range_init_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, pressure_range_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, extrapolation_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, advect_velocity_kernel<0>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, advect_velocity_kernel<1>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, advect_smoke_kernel<0>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, advect_smoke_kernel<1>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, sample_velocity_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, pack_rows_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, build_flags_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, export_masks_kernel);
+  return e == cudaSuccess ? SAYAL_OK : set_error(SAYAL_ECUDA, cudaGetErrorString(e));
+}
+
 }  // namespace sayal

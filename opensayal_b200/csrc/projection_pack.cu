@@ -989,6 +989,11 @@ int tiled_max_temporal_block() { return kMaxT; }
 // must never meet that wait in the middle of a step (its neighbour may be spinning for it), so every variant is
 // loaded when the sim is created.
 int tiled_preload() {
+  {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, tile_cost_kernel) != cudaSuccess || cudaFuncGetAttributes(&fa, tile_order_kernel) != cudaSuccess)
+      return set_error(SAYAL_ECUDA, "preload: tile order kernels");
+  }
   for (int v = 0; v < kNumVariants; v++)
     for (int m = 0; m < 5; m++) {
       cudaFuncAttributes fa;

@@ -8,6 +8,25 @@
 
 #include "sayal_internal.h"
 
+// measurement aids of sayal_stream_delay / sayal_stream_hold (defined here so that create_impl can preload them)
+__global__ void stream_delay_kernel(long long ns) {
+  long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  } while (t - t0 < ns);
+}
+
+__global__ void stream_gate_kernel(const volatile unsigned* gate, unsigned ticket) {
+  long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while ((int)(*gate - ticket) < 0) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > 20000000000ll) break;
+    __nanosleep(200);
+  }
+}
+
 namespace sayal {
 
 static thread_local std::string g_last_error;
@@ -237,6 +256,15 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   r = launch_build_geo(s);
   if (r != SAYAL_OK) return fail(r);
   r = tiled_preload();
+  if (r == SAYAL_OK) r = preload_basic();
+  if (r == SAYAL_OK) r = preload_advect();
+  if (r == SAYAL_OK) r = preload_slab();
+  if (r == SAYAL_OK) r = preload_visual();
+  if (r == SAYAL_OK) {  // this file's own kernels
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, stream_delay_kernel) != cudaSuccess || cudaFuncGetAttributes(&fa, stream_gate_kernel) != cudaSuccess)
+      r = set_error(SAYAL_ECUDA, "preload: stream kernels");
+  }
   if (r != SAYAL_OK) return fail(r);
   e = cudaStreamSynchronize(s->stream);
   if (e != cudaSuccess) return fail(set_error(SAYAL_ECUDA, cudaGetErrorString(e)));
@@ -1057,14 +1085,6 @@ int sayal_debug_timeline(sayal_sim* sim, int64_t* host_dst, int32_t max_tiles, i
 
 // Measurement aid: hold the sim's stream for `microseconds` (one thread spinning on %globaltimer), so that a caller
 // can enqueue a whole timed region before the device starts on it and host jitter cannot drain the queue.
-__global__ void stream_delay_kernel(long long ns) {
-  long long t0, t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  do {
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  } while (t - t0 < ns);
-}
-
 int sayal_stream_delay(sayal_sim* sim, int64_t microseconds) {
   if (!sim || microseconds < 0 || microseconds > 1000000) return set_error(SAYAL_EINVAL, "sayal_stream_delay: 0..1e6 us");
   Sim* s = S(sim);
@@ -1074,20 +1094,21 @@ int sayal_stream_delay(sayal_sim* sim, int64_t microseconds) {
   return SAYAL_OK;
 }
 
+int sayal_debug_link_words(sayal_sim* sim, uint32_t* host_dst) {
+  if (!sim || !host_dst) return set_error(SAYAL_EINVAL, "sayal_debug_link_words: null argument");
+  Sim* s = S(sim);
+  if (!s->link_block || !s->link_counters) return set_error(SAYAL_EINVAL, "sayal_debug_link_words: the sim has no slab link");
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  CUDA_TRY(cudaMemcpy(host_dst, s->link_block, LW_WORDS * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(host_dst + LW_WORDS, s->link_counters, 32 * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  return SAYAL_OK;
+}
+
 // Host-released gate: a one-thread kernel on the sim's stream spins on a word in mapped host memory until
 // sayal_stream_release stores the matching ticket.  Everything enqueued behind it starts exactly when the host says
 // so — a measured region can be enqueued completely, the ranks of a multi-GPU run can meet at a host barrier, and
 // only then do the devices begin.  The spin gives up after 20 s (a forgotten release must not wedge the GPU).
-__global__ void stream_gate_kernel(const volatile unsigned* gate, unsigned ticket) {
-  long long t0, t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  while ((int)(*gate - ticket) < 0) {
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    if (t - t0 > 20000000000ll) break;
-    __nanosleep(200);
-  }
-}
-
 int sayal_stream_hold(sayal_sim* sim) {
   if (!sim) return set_error(SAYAL_EINVAL, "sayal_stream_hold: null sim");
   Sim* s = S(sim);

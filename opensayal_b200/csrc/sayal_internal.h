@@ -267,6 +267,10 @@ int tiled_max_temporal_block();
 int tiled_debug_pass_plans(int pitch, int local_rows, int own_lo, int own_hi, int rows_per_warp, int T, int iterations,
                            int ghost_depth, int32_t* out, int capacity);  // host only; 15 int32 per pass, see sayal.h
 int tiled_push_temporal_block(int iterations, int halo);  // push mode: the T every rank of a chain uses
+int preload_basic();   // each file's kernels, loaded at sayal_create (see tiled_preload)
+int preload_advect();
+int preload_slab();
+int preload_visual();
 int tiled_preload();  // load every kernel variant now (never lazily in the middle of a linked step)
 int tiled_prepare(Sim* s, int iterations);  // choose the tile plan (may time candidates; not capturable)
 int tiled_prepare_windows(Sim* s, int iterations, int ghost_depth);  // + the issue orders of a linked slab's row windows

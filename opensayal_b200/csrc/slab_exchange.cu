@@ -342,4 +342,15 @@ int launch_slab_push_wait(Sim* s, int passes, int signature) {
   return SAYAL_OK;
 }
 
+// Load this file's kernels now: CUDA loads a kernel lazily at its first launch, and that load can wait for the device
+// to drain — which never happens while a linked slab on the same device spins for rows this thread has yet to enqueue.
+int preload_slab() {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, slab_exchange_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, slab_range_reduce_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, slab_push_wait_kernel);
+  return e == cudaSuccess ? SAYAL_OK : set_error(SAYAL_ECUDA, cudaGetErrorString(e));
+}
+
 }  // namespace sayal

@@ -234,4 +234,16 @@ int launch_arrows(Sim* s, const sayal_visual* v, int nx, int ny, sayal_arrow* d_
   return SAYAL_OK;
 }
 
+// Load this file's kernels now: CUDA loads a kernel lazily at its first launch, and that load can wait for the device
+// to drain — which never happens while a linked slab on the same device spins for rows this thread has yet to enqueue.
+int preload_visual() {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, render_pixels_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, diffusion_half_sweep_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, path_lines_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, arrows_kernel);
+  return e == cudaSuccess ? SAYAL_OK : set_error(SAYAL_ECUDA, cudaGetErrorString(e));
+}
+
 }  // namespace sayal

@@ -352,6 +352,12 @@ class Fluid:
         check(self._lib.sayal_debug_timeline(self._sim, out.ctypes.data_as(C.c_void_p), max_tiles, C.byref(n)))
         return out[: n.value]
 
+    def debug_link_words(self) -> np.ndarray:
+        """Diagnostics: 64 control words of the slab link + 32 private counters (csrc/sayal_internal.h)."""
+        out = np.zeros(96, dtype=np.uint32)
+        check(self._lib.sayal_debug_link_words(self._sim, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def stream_delay(self, microseconds: int) -> None:
         """Measurement aid: hold the sim's stream so that a timed region can be enqueued ahead of the device."""
         check(self._lib.sayal_stream_delay(self._sim, int(microseconds)))
