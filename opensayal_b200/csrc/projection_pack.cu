@@ -152,6 +152,24 @@ struct PushArgs {
   int* link_error;
 };
 
+// Resident mode (whole domains whose tiles all fit on the GPU at once, one per SM): ONE launch runs the whole
+// projection.  Every tile stays in its CTA's registers from the first iteration to the last; between sweep blocks of
+// `T` iterations the CTAs trade only what the trapezoid argument says has gone stale — the ring of owned cells within
+// one halo of a tile edge — instead of storing and re-loading the whole domain once per pass.  No grid barrier and no
+// flags: the rings travel as 8-byte words {value, tag} (a naturally aligned 8-byte store is single-copy atomic), the
+// tag counts exchanges, and a reader simply re-reads a word until its tag is the one it waits for — the latency of an
+// exchange is one store and one load through L2, with no fence in between.  A word sits at its cell's own place in a
+// full-size mailbox array; two mailboxes alternate (exchange parity) so that a ring is never stored over one a
+// neighbour may still be reading: a tile can only store exchange k + 2 after it has read its neighbours' exchange
+// k + 1, which they stored after they had read its exchange k.
+struct ResidentArgs {
+  int blocks;        // sweep blocks (exchanges + 1); 0 = not resident
+  unsigned* epoch;   // [0] value the tags of this launch count from, [1] ticket of finished tiles
+  int* error;        // mapped host word, raised if a neighbour never shows up (the launch is cooperative: cannot happen)
+  u64* box_u[2];     // mailboxes by exchange parity, pitch x local_rows words each
+  u64* box_v[2];
+};
+
 struct PackArgs {
   Grid g;
   const float* __restrict__ u_in;
@@ -181,6 +199,7 @@ struct PackArgs {
   int write_lo, write_hi;  // rows this pass may write: the window, or (push mode) the owned rows only — the ghost
                            // rows of the output arrays belong to the neighbours' pushes
   PushArgs push;
+  ResidentArgs res;
   int tiles_x;           // tiles per tile row (the grid is one-dimensional: blockIdx.x -> order -> tile)
   const int* order;      // tiles sorted by cost, most expensive first (tile_order_kernel), or null for row-major
   int extrap_on;  // the step's last pass: apply_extrapolation_at (fluid.cu:720-733) on the tile before it is stored
@@ -239,6 +258,40 @@ __device__ __forceinline__ long long globaltimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+
+// Tagged words of the resident ring exchange: {value, tag} pairs, two per 16-byte access (each 64-bit element of a
+// .v2.b64 access is single-copy atomic; relaxed gpu-scope accesses go through L2, never a stale L1 line).
+__device__ __forceinline__ void box_store2(u64* p, float a, float b, unsigned tag) {
+  const u64 t = (u64)tag << 32;
+  asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(t | __float_as_uint(a)), "l"(t | __float_as_uint(b)) : "memory");
+}
+__device__ __forceinline__ void box_load2(const u64* p, u64& a, u64& b) {
+  asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+
+// Geometry of a resident tile's halo (held, owned by a neighbour): a top and a bottom band of whole rows and a left and
+// a right band beside the owned rows.  The halo is fetched by ALL threads of the CTA in 2-cell chunks (one 16-byte
+// tagged load each, every load independent) into a staging area in shared memory laid out band by band; the threads
+// that hold halo cells then pick theirs up with one 16-byte shared load per row and field.
+struct HaloBands {
+  int X0, Y0, ox0, ox1, oy0, oy1;  // tile origin, owned columns [ox0, ox1) and rows [oy0, oy1)
+  int tw2, hl2, hr2;               // chunks per row of the whole-row bands / the left band / the right band
+  int base_b, base_l, base_r, total;  // first chunk of the bottom / left / right band, chunks per field
+  // chunk index of cells (lr, x), (lr, x + 1); x - X0 is even
+  __device__ __forceinline__ int encode(int lr, int x) const {
+    if (lr < oy0) return (lr - Y0) * tw2 + ((x - X0) >> 1);
+    if (lr >= oy1) return base_b + (lr - oy1) * tw2 + ((x - X0) >> 1);
+    if (x < ox0) return base_l + (lr - oy0) * hl2 + ((x - X0) >> 1);
+    return base_r + (lr - oy0) * hr2 + ((x - ox1) >> 1);
+  }
+  // local row and first column of chunk c
+  __device__ __forceinline__ void decode(int c, int& lr, int& x) const {
+    if (c < base_b) { lr = Y0 + c / tw2; x = X0 + 2 * (c % tw2); }
+    else if (c < base_l) { c -= base_b; lr = oy1 + c / tw2; x = X0 + 2 * (c % tw2); }
+    else if (c < base_r) { c -= base_l; lr = oy0 + c / hl2; x = X0 + 2 * (c % hl2); }
+    else { c -= base_r; lr = oy0 + c / hr2; x = ox1 + 2 * (c % hr2); }
+  }
+};
 
 // One row of one half-sweep.  C = 0: columns (0,2) are the active colour, C = 1: columns (1,3).
 // vt / vb are the v faces above / below the row for the active columns.
@@ -334,7 +387,9 @@ __device__ __forceinline__ void half_sweep(u64 (&U02)[RY], u64 (&U13)[RY], u64 (
 // rows) and accumulates one FMA per cell update.  p is updated IN PLACE in global memory: a cell's p is written
 // only by the tile that owns it, which read it when the pass began; what other tiles read in their halo never
 // leaves them, and nothing else depends on p.
-template <int RY, int NW, bool FORCES, bool EXTRAP, bool PRESSURE>
+// RESIDENT: the whole projection in one launch, tiles kept in registers between sweep blocks (ResidentArgs); forces and
+// extrapolation are compiled in and switched by a.force_on / a.extrap_on.
+template <int RY, int NW, bool FORCES, bool EXTRAP, bool PRESSURE, bool RESIDENT = false>
 __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a) {
   extern __shared__ __align__(16) float sp[];  // PRESSURE only
   constexpr int TH = RY * NW;
@@ -354,7 +409,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   const int X0 = tile_x * a.stride_x, Y0 = a.row_lo + tile_y * a.stride_y;
   const int x = X0 + 4 * lane;
   const int lr0 = Y0 + w * RY;
-  long long* tl = a.timeline ? a.timeline + 5 * (size_t)tile : nullptr;
+  long long* tl = a.timeline && !RESIDENT ? a.timeline + 5 * (size_t)tile : nullptr;
   if (tl && threadIdx.x == 0) {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -433,7 +488,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
       sts64(sp_warp + r * 128 + 64, pk(pv.y, pv.w));
     }
   }
-  if (FORCES) {
+  if (FORCES && (!RESIDENT || a.force_on)) {
     // Forces on the register tile, AFTER the loop above: anything with control flow between the loads would keep
     // the compiler from issuing them back to back (measured: +5 us per pass).
     const u64 G2 = pk(a.force_g, a.force_g), DT2 = pk(a.force_dt, a.force_dt);
@@ -485,7 +540,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
     float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (col_ok && Y0 - 1 >= a.row_lo && Y0 - 1 < a.row_hi) {
       vv = __ldcg(reinterpret_cast<const float4*>(a.v_in + (size_t)(Y0 - 1) * g.pitch + x));
-      if (FORCES) {
+      if (FORCES && (!RESIDENT || a.force_on)) {
         float4 unused = make_float4(0.f, 0.f, 0.f, 0.f);
         forces_on_load(a, x, Y0 - 1, unused, vv);
       }
@@ -534,33 +589,164 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   const int j0 = g.H - 1 - (g.row_base + lr0);
   const int q = j0 & 1;  // case of row 0 in the first (even) half-sweep: 0 -> columns (0,2)
   static_assert(RY % 2 == 0, "rows per warp must be even: q must be uniform across the CTA's warps");
-  if (!irr) {
-    for (int it = 0; it < a.iters; it++) {
-      if (q == 0) {
-        half_sweep<RY, 0, false, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-        __syncthreads();
-        half_sweep<RY, 1, false, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-        __syncthreads();
-      } else {
-        half_sweep<RY, 1, false, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-        __syncthreads();
-        half_sweep<RY, 0, false, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-        __syncthreads();
+  __shared__ unsigned s_res_base;
+  if (RESIDENT && threadIdx.x == 0) s_res_base = __ldcg(a.res.epoch);  // advanced by the last tile to finish, i.e. after
+                                                                      // every tile has read it; visible to the CTA after
+                                                                      // the first barrier of the sweeps
+  const int nblk = RESIDENT ? a.res.blocks : 1;
+  const int it_base = a.iters / nblk, it_long = a.iters % nblk;
+  for (int blk = 0; blk < nblk; blk++) {
+    const int its = it_base + (blk < it_long ? 1 : 0);
+    // profiling only (option "debug_timeline"): six stamps per tile and block — sweeps begin, sweeps done, ring stored,
+    // flag published, neighbours' flags seen, halo loaded
+    long long* rtl = RESIDENT && a.timeline && threadIdx.x == 0 ? a.timeline + ((size_t)tile * nblk + blk) * 6 : nullptr;
+    if (rtl) rtl[0] = globaltimer();
+    if (!irr) {
+      for (int it = 0; it < its; it++) {
+        if (q == 0) {
+          half_sweep<RY, 0, false, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+          half_sweep<RY, 1, false, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+        } else {
+          half_sweep<RY, 1, false, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+          half_sweep<RY, 0, false, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+        }
+      }
+    } else {
+      for (int it = 0; it < its; it++) {
+        if (q == 0) {
+          half_sweep<RY, 0, true, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+          half_sweep<RY, 1, true, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+        } else {
+          half_sweep<RY, 1, true, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+          half_sweep<RY, 0, true, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+        }
       }
     }
-  } else {
-    for (int it = 0; it < a.iters; it++) {
-      if (q == 0) {
-        half_sweep<RY, 0, true, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-        __syncthreads();
-        half_sweep<RY, 1, true, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-        __syncthreads();
-      } else {
-        half_sweep<RY, 1, true, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-        __syncthreads();
-        half_sweep<RY, 0, true, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-        __syncthreads();
+    if (rtl) rtl[1] = globaltimer();
+    if (!RESIDENT || blk == nblk - 1) break;
+    // ---- ring exchange `blk`: my ring out, the neighbours' rings (my halo) in (protocol: ResidentArgs).
+    // Everything the exchange needs is recomputed here from the special registers (read through volatile asm, so that
+    // the compiler cannot share it with the prologue): nothing of it stays live across the sweeps, whose loop has no
+    // register to spare — spilled, it was re-read from local memory row by row, each read a trip to L2.
+    {
+      int rt_tile, rt_tid;
+      asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(rt_tile));
+      asm volatile("mov.u32 %0, %%tid.x;" : "=r"(rt_tid));
+      const int e_ty = rt_tile / a.tiles_x, e_tx = rt_tile - e_ty * a.tiles_x;
+      const int eX0 = e_tx * a.stride_x, eY0 = a.row_lo + e_ty * a.stride_y;
+      const int ex = eX0 + 4 * (rt_tid & 31), elr0 = eY0 + (rt_tid >> 5) * RY;
+      const int xe = eX0 + TW < g.pitch ? eX0 + TW : g.pitch, ye = eY0 + TH < a.row_hi ? eY0 + TH : a.row_hi;  // held extent
+      HaloBands hb;
+      hb.X0 = eX0; hb.Y0 = eY0;
+      hb.ox0 = eX0 == 0 ? 0 : eX0 + a.halo_x;
+      hb.ox1 = eX0 + TW >= g.pitch ? g.pitch : eX0 + TW - a.halo_x;
+      hb.oy0 = eY0 == a.row_lo ? a.row_lo : eY0 + a.halo_y;
+      hb.oy1 = eY0 + TH >= a.row_hi ? a.row_hi : eY0 + TH - a.halo_y;
+      hb.tw2 = (xe - eX0) >> 1; hb.hl2 = (hb.ox0 - eX0) >> 1; hb.hr2 = (xe - hb.ox1) >> 1;
+      hb.base_b = (hb.oy0 - eY0) * hb.tw2;
+      hb.base_l = hb.base_b + (ye - hb.oy1) * hb.tw2;
+      hb.base_r = hb.base_l + (hb.oy1 - hb.oy0) * hb.hl2;
+      hb.total = hb.base_r + (hb.oy1 - hb.oy0) * hb.hr2;
+      // ring: owned cells within one halo of an owned edge that has a neighbour (what the neighbours' halos hold);
+      // halo: held cells a neighbour owns
+      const bool lane_held = ex < xe, lane_owned = ex >= hb.ox0 && ex < hb.ox1;
+      const bool lane_ring = lane_owned && ((eX0 != 0 && ex < hb.ox0 + a.halo_x) || (eX0 + TW < g.pitch && ex >= hb.ox1 - a.halo_x));
+      const int ring_t = eY0 != a.row_lo ? hb.oy0 + a.halo_y : hb.oy0;       // owned rows below this one are not top ring
+      const int ring_b = eY0 + TH < a.row_hi ? hb.oy1 - a.halo_y : hb.oy1;  // owned rows from this one on are bottom ring
+
+      const int par = blk & 1;
+      const unsigned tag = s_res_base + 1u + (unsigned)blk;
+      u64* bu = a.res.box_u[par];
+      u64* bv = a.res.box_v[par];
+      vlast02 = lds64(sv_bot);  // my last row of v faces lives in shared memory during the sweeps
+      vlast13 = lds64(sv_bot + 64);
+      if (lane_owned) {
+#pragma unroll
+        for (int r = 0; r < RY; r++) {
+          const int lr = elr0 + r;
+          if (lr < hb.oy0 || lr >= hb.oy1 || !(lane_ring || lr < ring_t || lr >= ring_b)) continue;
+          const size_t k = (size_t)lr * g.pitch + ex;
+          const u64 p02 = r < RY - 1 ? V02[r < RY - 1 ? r : 0] : vlast02;
+          const u64 p13 = r < RY - 1 ? V13[r < RY - 1 ? r : 0] : vlast13;
+          box_store2(bu + k, lo(U02[r]), lo(U13[r]), tag);
+          box_store2(bu + k + 2, hi(U02[r]), hi(U13[r]), tag);
+          box_store2(bv + k, lo(p02), lo(p13), tag);
+          box_store2(bv + k + 2, hi(p02), hi(p13), tag);
+        }
       }
+      if (rtl) rtl[2] = globaltimer();
+      // every thread fetches its share of the halo's chunks (u then v), four loads in flight, re-reading a chunk until
+      // both of its tags are this exchange's
+      float* stage = sp;
+      const int total2 = 2 * hb.total;
+      long long t0 = 0;
+      for (int c0 = rt_tid; c0 < total2; c0 += 4 * NW * 32) {
+        u64 w0[4], w1[4];
+        const u64* src[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int c = c0 + k * NW * 32;
+          src[k] = nullptr;
+          if (c < total2) {
+            int lr, xx;
+            hb.decode(c < hb.total ? c : c - hb.total, lr, xx);
+            src[k] = (c < hb.total ? bu : bv) + (size_t)lr * g.pitch + xx;
+            box_load2(src[k], w0[k], w1[k]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (!src[k]) continue;
+          unsigned polls = 0;
+          while ((unsigned)(w0[k] >> 32) != tag || (unsigned)(w1[k] >> 32) != tag) {
+            box_load2(src[k], w0[k], w1[k]);
+            if ((++polls & 4095u) == 0) {  // half a second without an answer: a broken launch, do not wedge the GPU
+              const long long t = globaltimer();
+              if (t0 == 0) t0 = t;
+              if (t - t0 > 500000000ll) {
+                *reinterpret_cast<volatile int*>(a.res.error) = 1;
+                __threadfence_system();
+                break;
+              }
+            }
+          }
+          *reinterpret_cast<float2*>(stage + 2 * (c0 + k * NW * 32)) =
+              make_float2(__uint_as_float((unsigned)w0[k]), __uint_as_float((unsigned)w1[k]));
+        }
+      }
+      __syncthreads();
+      if (rtl) rtl[4] = globaltimer();
+      if (lane_held) {
+#pragma unroll
+        for (int r = 0; r < RY; r++) {
+          const int lr = elr0 + r;
+          if (lr >= ye || (lane_owned && lr >= hb.oy0 && lr < hb.oy1)) continue;
+          const int c = hb.encode(lr, ex);
+          const float4 uu = *reinterpret_cast<const float4*>(stage + 2 * c);
+          const float4 vv = *reinterpret_cast<const float4*>(stage + 2 * (hb.total + c));
+          U02[r] = pk(uu.x, uu.z);
+          U13[r] = pk(uu.y, uu.w);
+          if (r < RY - 1) {
+            V02[r < RY - 1 ? r : 0] = pk(vv.x, vv.z);
+            V13[r < RY - 1 ? r : 0] = pk(vv.y, vv.w);
+          } else {
+            vlast02 = pk(vv.x, vv.z);
+            vlast13 = pk(vv.y, vv.w);
+          }
+        }
+      }
+      sts64(sv_bot, vlast02);
+      sts64(sv_bot + 64, vlast13);
+      __syncthreads();  // the warp below reads these faces in its next half-sweep; the staging area is free again
+      if (rtl) rtl[5] = globaltimer();
     }
   }
 
@@ -572,7 +758,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   // j-rules, then all i-rules; see extrapolation_kernel in kernels_basic.cu) applied to the registers.  Every
   // source value sits in the same tile as its destination: rows j = 0, 1 (and H-1, H-2) are the last (first) two
   // rows of the domain, inside the un-haloed edge of the tiles that hold them; columns 0, 1 share a lane.
-  if (EXTRAP) {
+  if (EXTRAP && (!RESIDENT || a.extrap_on)) {
     const int lrA = g.H - 2 - g.row_base, lrB = lrA + 1;  // memory rows of j = 1 and j = 0
     // u(i, H-1) = u(i, H-2): memory rows 0 and 1, both rows of warp 0 of the top tiles
     if (g.row_base == 0 && Y0 == 0 && w == 0 && a.row_hi >= 2) {
@@ -674,6 +860,13 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
       }
     }
   }
+  if (RESIDENT) {  // the last tile to finish moves the epoch past every tag of this launch
+    if (threadIdx.x == 0 && atomicAdd(a.res.epoch + 1, 1u) == gridDim.x - 1) {
+      a.res.epoch[1] = 0;
+      __threadfence();
+      a.res.epoch[0] = s_res_base + (unsigned)nblk + 1u;
+    }
+  }
   if (tl) {
     __syncthreads();
     if (threadIdx.x == 0) tl[3] = globaltimer();
@@ -733,12 +926,13 @@ __global__ void tile_order_kernel(const int* __restrict__ cost, int tiles, int* 
 
 struct Variant {
   int ry, nw;
-  void (*kernel[5])(PackArgs);  // indexed by (forces on load) | (extrapolation before store) << 1; [4] = with pressure
+  void (*kernel[6])(PackArgs);  // indexed by (forces on load) | (extrapolation before store) << 1; [4] = with pressure;
+                                // [5] = resident (whole projection in one launch, forces / extrapolation by flag)
 };
 #define SAYAL_PACK_VARIANT(RY, NW)                                                                                        \
   {RY, NW, {projection_pack_kernel<RY, NW, false, false, false>, projection_pack_kernel<RY, NW, true, false, false>,     \
             projection_pack_kernel<RY, NW, false, true, false>, projection_pack_kernel<RY, NW, true, true, false>,       \
-            projection_pack_kernel<RY, NW, false, false, true>}}
+            projection_pack_kernel<RY, NW, false, false, true>, projection_pack_kernel<RY, NW, true, true, false, true>}}
 const Variant kVariants[] = {SAYAL_PACK_VARIANT(8, 16), SAYAL_PACK_VARIANT(10, 16), SAYAL_PACK_VARIANT(12, 16)};
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kMaxT = 16;
@@ -897,8 +1091,113 @@ int push_sides_of(const Sim* s) {
   return (s->link.peer_words[0] ? 1 : 0) | (s->link.peer_words[1] ? 2 : 0);
 }
 
+// Resident mode (ResidentArgs): is it possible for this sim / plan, and the launch itself.
+constexpr size_t kResidentStageMax = 176 * 1024;  // dynamic shared memory a resident launch may ask for
+
+bool resident_possible(const Sim* s) {
+  return s->resident && s->d_resident && !s->ph.enable_pressure && s->g.local_rows == s->g.H;
+}
+
+// bytes of shared staging for the halo of one tile: 2 fields x 4 bytes per halo cell (upper bound: an interior tile)
+size_t resident_stage_bytes(const Variant& v, const Geometry& q) {
+  const size_t held = (size_t)TW * v.ry * v.nw, owned = (size_t)q.stride_x * q.stride_y;
+  return 8 * (held - owned);
+}
+
+bool resident_geometry(const Sim* s, const Variant& v, int T, Geometry* q) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+  return geometry(s->g, v, T, q) && q->tiles_x * q->tiles_y <= sms && resident_stage_bytes(v, *q) <= kResidentStageMax;
+}
+
+// The four mailbox arrays (two parities x u, v; 8 bytes per cell), allocated the first time a resident plan is
+// considered (never while a graph is being captured: plans are chosen before).
+bool resident_mailboxes(Sim* s) {
+  if (s->d_box) return true;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s->stream, &cap);
+  if (cap != cudaStreamCaptureStatusNone) return false;
+  const size_t words = (size_t)s->g.pitch * s->g.local_rows;
+  if (cudaMalloc(&s->d_box, 4 * words * sizeof(u64)) != cudaSuccess) {
+    cudaGetLastError();
+    s->d_box = nullptr;
+    return false;
+  }
+  cudaMemsetAsync(s->d_box, 0, 4 * words * sizeof(u64), s->stream);  // tag 0: never a tag of an exchange
+  return true;
+}
+
+int run_resident(Sim* s, int variant, int T, int iterations, float d_t, bool with_forces, bool with_extrap) {
+  const Variant& v = kVariants[variant];
+  Geometry q;
+  if (!resident_possible(s) || !resident_geometry(s, v, T, &q))
+    return set_error(SAYAL_EINVAL, "resident projection: the tiles of this plan do not fit on the GPU at once");
+  PackArgs a = {};
+  a.g = s->g;
+  a.row_lo = a.write_lo = 0;
+  a.row_hi = a.write_hi = s->g.local_rows;
+  a.u_in = s->u; a.v_in = s->v; a.u_out = s->u_buf; a.v_out = s->v_buf;
+  a.flags = s->flags;
+  a.o = s->ph.o;
+  a.iters = iterations;
+  a.halo_x = q.halo_x; a.halo_y = q.halo_y; a.stride_x = q.stride_x; a.stride_y = q.stride_y;
+  a.density = s->ph.density;
+  a.hf = (float)s->g.h;
+  a.inv_dt = 1.0f / d_t;
+  a.extrap_on = with_extrap;
+  a.force_on = with_forces;
+  a.smoke = s->smoke;
+  if (a.force_on) {
+    const ForceArgs& f = s->fuse_args;
+    const Phys& ph = s->ph;
+    a.force_g = ph.g; a.force_dt = f.d_t; a.wt_speed = ph.wt_speed; a.wt_smoke = ph.wt_smoke;
+    a.inlet_len = ph.wt_smoke_length; a.band_lo = f.band_lo; a.band_hi = f.band_hi;
+    a.smoke_lo = f.smoke_lo; a.smoke_hi = f.smoke_hi; a.smoke_count = ph.wt_smoke_count;
+    a.smoke_height = ph.wt_smoke_height; a.period = f.period; a.anchor = f.anchor;
+  }
+  a.tiles_x = q.tiles_x;
+  if (!s->d_box) return set_error(SAYAL_EINVAL, "resident projection: no mailboxes (plan chosen without them?)");
+  a.res.blocks = (iterations + T - 1) / T;
+  a.res.epoch = s->d_resident;
+  a.res.error = s->d_resident_error;
+  {
+    const size_t words = (size_t)s->g.pitch * s->g.local_rows;
+    u64* box = reinterpret_cast<u64*>(s->d_box);
+    a.res.box_u[0] = box; a.res.box_v[0] = box + words;
+    a.res.box_u[1] = box + 2 * words; a.res.box_v[1] = box + 3 * words;
+  }
+  {  // profiling only: 6 stamps per tile and block, read back through sayal_debug_timeline as rows of 5 int64
+    const size_t stamps = (size_t)q.tiles_x * q.tiles_y * a.res.blocks * 6;
+    a.timeline = s->d_timeline && stamps <= s->timeline_cap ? s->d_timeline : nullptr;
+    s->timeline_tiles = a.timeline ? (int)((stamps + 4) / 5) : 0;
+  }
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(q.tiles_x * q.tiles_y);
+  lc.blockDim = dim3(v.nw * 32);
+  lc.dynamicSmemBytes = resident_stage_bytes(v, q);
+  lc.stream = s->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // every tile on an SM at once: the tiles wait for each other
+  attr[0].val.cooperative = 1;
+  lc.attrs = attr;
+  lc.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&lc, v.kernel[5], a);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    char m[256];
+    snprintf(m, sizeof m, "projection_pack_kernel (resident): %s", cudaGetErrorString(e));
+    return set_error(SAYAL_ECUDA, m);
+  }
+  s->launches++;
+  float* t = s->u; s->u = s->u_buf; s->u_buf = t;
+  t = s->v; s->v = s->v_buf; s->v_buf = t;
+  s->parity ^= 1;
+  return SAYAL_OK;
+}
+
 int run_passes(Sim* s, int variant, int T, int iterations, float d_t, bool with_forces = false, bool with_extrap = false,
-               int ghost_depth = -1, int push_sides = 0) {
+               int ghost_depth = -1, int push_sides = 0, bool resident = false) {
+  if (resident) return run_resident(s, variant, T, iterations, d_t, with_forces, with_extrap);
   const Variant& v = kVariants[variant];
   static thread_local PassPlan plans[kMaxPasses];
   const int passes = make_pass_plans(s->g, v, T, iterations, ghost_depth, push_sides, s->slab_halo, plans, kMaxPasses);
@@ -995,11 +1294,13 @@ int tiled_preload() {
       return set_error(SAYAL_ECUDA, "preload: tile order kernels");
   }
   for (int v = 0; v < kNumVariants; v++)
-    for (int m = 0; m < 5; m++) {
+    for (int m = 0; m < 6; m++) {
       cudaFuncAttributes fa;
       cudaError_t e = cudaFuncGetAttributes(&fa, kVariants[v].kernel[m]);
       if (e == cudaSuccess && m == 4)
         e = cudaFuncSetAttribute(kVariants[v].kernel[4], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pressure_smem(kVariants[v]));
+      if (e == cudaSuccess && m == 5)
+        e = cudaFuncSetAttribute(kVariants[v].kernel[5], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResidentStageMax);
       if (e != cudaSuccess) return set_error(SAYAL_ECUDA, cudaGetErrorString(e));
     }
   return SAYAL_OK;
@@ -1011,10 +1312,13 @@ int tiled_preload() {
 int tiled_prepare(Sim* s, int iterations) {
   if (iterations <= 0) return SAYAL_OK;
   const int push = push_sides_of(s) ? 1 : 0;
+  const int want_resident = resident_possible(s) && !push && resident_mailboxes(s) ? 1 : 0;
   for (int k = 0; k < s->n_plans; k++)
-    if (s->plans[k].iterations == iterations && s->plans[k].push == push) {  // slab runs alternate between chunk sizes: keep every plan
+    if (s->plans[k].iterations == iterations && s->plans[k].push == push && s->plans[k].resident_ok == want_resident) {
+      // (slab runs alternate between chunk sizes: keep every plan)
       s->plan_variant = s->plans[k].variant;
       s->plan_T = s->plans[k].T;
+      s->plan_resident = s->plans[k].resident;
       return SAYAL_OK;
     }
   // the temporal block is given (option), dictated by the chain (push mode: every rank must split alike), or tuned
@@ -1023,8 +1327,8 @@ int tiled_prepare(Sim* s, int iterations) {
   else if (push) forced_T = tiled_push_temporal_block(iterations, s->slab_halo);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-  struct Cand { int variant, T; double cost; float ms; };
-  Cand cands[kNumVariants * kMaxT];
+  struct Cand { int variant, T; double cost; float ms; int resident; };
+  Cand cands[2 * kNumVariants * kMaxT];
   int nc = 0;
   for (int v = 0; v < kNumVariants; v++)
     for (int T = 1; T <= kMaxT && T <= iterations; T++) {
@@ -1035,7 +1339,13 @@ int tiled_prepare(Sim* s, int iterations) {
         if (forced_T <= 0 && (iterations + passes - 1) / passes != T) continue;
       }
       double c = model_cost(s->g, kVariants[v], T, iterations, sms);
-      if (c < 1e29) cands[nc++] = {v, T, c, 0.f};
+      if (c < 1e29 && !(want_resident && s->resident == 2)) cands[nc++] = {v, T, c, 0.f, 0};  // resident = 2: resident plans only
+      Geometry q;
+      if (want_resident && resident_geometry(s, kVariants[v], T, &q)) {
+        // one load / store of the tile, `blocks` sweep blocks, blocks - 1 ring exchanges of about a microsecond
+        const int blocks = (iterations + T - 1) / T;
+        cands[nc++] = {v, T, kVariants[v].ry * (0.45 + 0.13 * iterations) + 1.25 * (blocks - 1), 0.f, 1};
+      }
     }
   if (nc == 0) return set_error(SAYAL_EINVAL, "projection tile: no feasible tile plan");
   for (int a = 0; a < nc; a++)  // selection sort by model cost
@@ -1065,7 +1375,7 @@ int tiled_prepare(Sim* s, int iterations) {
       // one timed run of a candidate (ms), or a negative value on failure
       auto time_once = [&](const Cand& c) -> float {
         cudaEventRecord(e0, s->stream);
-        int r = run_passes(s, c.variant, c.T, iterations, 1.0f);
+        int r = run_passes(s, c.variant, c.T, iterations, 1.0f, false, false, -1, 0, c.resident != 0);
         cudaEventRecord(e1, s->stream);
         if (r != SAYAL_OK || cudaEventSynchronize(e1) != cudaSuccess) return -1.f;
         float ms = 0.f;
@@ -1131,24 +1441,26 @@ int tiled_prepare(Sim* s, int iterations) {
   }
   s->plan_variant = cands[best].variant;
   s->plan_T = cands[best].T;
+  s->plan_resident = cands[best].resident;
   {  // what was considered, for the bench line and for anyone who wonders why this plan (sayal_plan_log)
-    int at = snprintf(s->plan_log, sizeof s->plan_log, "n=%d %s%s: rows T model ms\n", iterations, timed ? "timed" : "model only",
+    int at = snprintf(s->plan_log, sizeof s->plan_log, "n=%d %s%s: rows T[R = resident] model ms\n", iterations, timed ? "timed" : "model only",
                       push ? ", push mode" : "");
     for (int c = 0; c < nc && at < (int)sizeof s->plan_log - 48; c++) {
       if (timed && cands[c].ms > 1e29f) continue;
-      at += snprintf(s->plan_log + at, sizeof s->plan_log - at, "%c %d %d %.1f %.4f\n", c == best ? '*' : ' ',
-                     kVariants[cands[c].variant].ry, cands[c].T, cands[c].cost, timed ? cands[c].ms : 0.f);
+      at += snprintf(s->plan_log + at, sizeof s->plan_log - at, "%c %d %d%s %.1f %.4f\n", c == best ? '*' : ' ',
+                     kVariants[cands[c].variant].ry, cands[c].T, cands[c].resident ? "R" : "", cands[c].cost,
+                     timed ? cands[c].ms : 0.f);
     }
   }
   {  // the issue orders of the plan's pass geometries, now (they cannot be built while a graph is captured)
     const int passes = (iterations + s->plan_T - 1) / s->plan_T;
-    for (int it = iterations / passes; it <= (iterations + passes - 1) / passes; it++) {
+    for (int it = iterations / passes; !s->plan_resident && it <= (iterations + passes - 1) / passes; it++) {
       Geometry q;
       if (it > 0 && geometry(s->g, kVariants[s->plan_variant], it, &q)) tile_order(s, s->plan_variant, it, q, 0, s->g.local_rows);
     }
   }
   if (s->n_plans == Sim::kMaxPlans) s->n_plans = 0;  // full: start over (never happens with <= 8 chunk sizes)
-  s->plans[s->n_plans++] = {iterations, s->plan_variant, s->plan_T, push};
+  s->plans[s->n_plans++] = {iterations, s->plan_variant, s->plan_T, push, s->plan_resident, want_resident};
   return SAYAL_OK;
 }
 
@@ -1202,7 +1514,8 @@ int launch_projection_tiled(Sim* s, int iterations, float d_t) {
   s->fuse_extrap = with_extrap ? 2 : 0;  // 2 = done: the caller skips the extrapolation kernel
   const int depth = s->proj_depth;
   s->proj_depth = -1;
-  return run_passes(s, s->plan_variant, s->plan_T, iterations, d_t, with_forces, with_extrap, depth, push_sides_of(s));
+  return run_passes(s, s->plan_variant, s->plan_T, iterations, d_t, with_forces, with_extrap, depth, push_sides_of(s),
+                    s->plan_resident != 0);
 }
 
 // Push mode: the temporal block every rank of a chain uses for `iterations` iterations with `halo` ghost rows.  It

@@ -71,6 +71,9 @@ static void free_sim(Sim* s) {
   if (s->d_total_s) cudaFree(s->d_total_s);
   if (s->d_range) cudaFree(s->d_range);
   if (s->d_overflow) cudaFree(s->d_overflow);
+  if (s->d_resident) cudaFree(s->d_resident);
+  if (s->d_box) cudaFree(s->d_box);
+  if (s->h_resident_error) cudaFreeHost(s->h_resident_error);
   if (s->d_timeline) cudaFree(s->d_timeline);
   for (int k = 0; k < 2; k++) {
     if (s->ipc_opened[k]) cudaIpcCloseMemHandle(s->ipc_opened[k]);
@@ -187,6 +190,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   s->advect_kernel = 2;
   s->overlap_exchange = 1;
   s->slab_push = 1;
+  s->resident = 1;
   s->advect_margin = 16;
   s->autotune = 1;
   s->plan_variant = -1, s->n_plans = 0;
@@ -198,6 +202,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   if (const char* e = getenv("SAYAL_TILE_ROWS")) { int r = atoi(e); if (r == 8 || r == 10 || r == 12) s->force_variant = (r - 8) / 2; }
   if (const char* e = getenv("SAYAL_PROJECTION_KERNEL")) s->projection_kernel = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_USE_GRAPH")) s->use_graph = atoi(e) != 0;
+  if (const char* e = getenv("SAYAL_RESIDENT")) { int r = atoi(e); if (r >= 0 && r <= 2) s->resident = r; }
   if (const char* e = getenv("SAYAL_ADVECT_KERNEL")) { int k = atoi(e); if (k >= 0 && k <= 2) s->advect_kernel = k; }
   if (const char* e = getenv("SAYAL_ADVECT_MARGIN")) { int m = atoi(e); if (m >= 2) s->advect_margin = m; }
   if (const char* e = getenv("SAYAL_OVERLAP_EXCHANGE")) s->overlap_exchange = atoi(e) != 0;
@@ -249,6 +254,15 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   e = cudaMalloc(&s->d_overflow, sizeof(int32_t));
   if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
   cudaMemsetAsync(s->d_overflow, 0, sizeof(int32_t), s->stream);
+  // resident projection (projection_pack.cu): epoch + ticket; error word on the host
+  e = cudaMalloc(&s->d_resident, 8 * sizeof(unsigned));
+  if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
+  cudaMemsetAsync(s->d_resident, 0, 8 * sizeof(unsigned), s->stream);
+  e = cudaHostAlloc(reinterpret_cast<void**>(&s->h_resident_error), sizeof(int), cudaHostAllocMapped);
+  if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
+  *s->h_resident_error = 0;
+  e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&s->d_resident_error), s->h_resident_error, 0);
+  if (e != cudaSuccess) return fail(set_error(SAYAL_ECUDA, cudaGetErrorString(e)));
   int r = launch_build_flags(s);
   if (r != SAYAL_OK) return fail(r);
   e = cudaMalloc(&s->geo, field_elems(s) * sizeof(uint16_t));
@@ -479,6 +493,11 @@ bool push_mode(const Sim* s) {
 
 // The sticky link error of a slab sim (mapped host word, written by the kernels), as an error code.
 static int link_status(const Sim* s, const char* where) {
+  if (s->h_resident_error && *reinterpret_cast<volatile int*>(s->h_resident_error) != 0) {
+    char m[256];
+    snprintf(m, sizeof m, "%s: a tile of the resident projection waited in vain for its neighbours; fields are not valid", where);
+    return set_error(SAYAL_ECUDA, m);
+  }
   if (!s->h_link_error || *reinterpret_cast<volatile int*>(s->h_link_error) == LINK_OK) return SAYAL_OK;
   char m[256];
   snprintf(m, sizeof m, "%s: slab link broken (%s); fields are not valid", where,
@@ -997,6 +1016,11 @@ int sayal_set_option(sayal_sim* sim, const char* key, int64_t value) {
     s->fuse_extrapolation = value != 0;
   } else if (!strcmp(key, "shrink_window")) {
     s->shrink_window = value != 0;
+  } else if (!strcmp(key, "resident")) {
+    if (value < 0 || value > 2) return set_error(SAYAL_EINVAL, "resident must be 0 (off), 1 (candidate) or 2 (resident plans only)");
+    s->resident = (int)value;
+    s->n_plans = 0;  // plans are chosen with or without resident candidates
+    invalidate_graphs(s);
   } else if (!strcmp(key, "slab_push")) {
     s->slab_push = value != 0;
     s->plan_variant = -1, s->n_plans = 0;
@@ -1030,6 +1054,8 @@ int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value) {
   else if (!strcmp(key, "order_tiles")) *value = s->order_tiles;
   else if (!strcmp(key, "shrink_window")) *value = s->shrink_window;
   else if (!strcmp(key, "slab_push")) *value = s->slab_push;
+  else if (!strcmp(key, "resident")) *value = s->resident;
+  else if (!strcmp(key, "plan_resident")) *value = s->plan_resident;
   else if (!strcmp(key, "push_mode")) *value = push_mode(s) ? 1 : 0;
   else if (!strcmp(key, "fuse_extrapolation")) *value = s->fuse_extrapolation;
   else if (!strcmp(key, "advect_kernel")) *value = s->advect_kernel;

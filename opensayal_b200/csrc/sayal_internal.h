@@ -92,6 +92,16 @@ __device__ __forceinline__ long long now_ns() {
   return t;
 }
 constexpr long long kSpinLimitNs = 2000000000ll;
+// The sticky error word of a slab link lives in DEVICE memory (every spin iteration of every waiting warp reads it:
+// as a mapped host word those reads crossed PCIe by the hundred and stretched every wait); the first error is
+// mirrored once into a mapped host word whose address sits two ints behind it, where the host reads it for free.
+__device__ __forceinline__ void raise_link_error(int* link_error, int code) {
+  if (atomicCAS(link_error, 0, code) == 0) {
+    int* host = *reinterpret_cast<int**>(link_error + 2);
+    if (host) *reinterpret_cast<volatile int*>(host) = code;
+  }
+  __threadfence_system();
+}
 // Spin until *word >= target (wrap-safe).  Gives up after two seconds, or at once when the link is already broken,
 // raising the sticky error word; returns false then.
 __device__ __forceinline__ bool spin_until(const unsigned* word, unsigned target, int* link_error) {
@@ -99,8 +109,7 @@ __device__ __forceinline__ bool spin_until(const unsigned* word, unsigned target
   const long long t0 = now_ns();
   while ((int)(ld_acquire_sys(word) - target) < 0) {
     if (now_ns() - t0 > kSpinLimitNs || *reinterpret_cast<volatile int*>(link_error) != 0) {
-      atomicCAS(link_error, 0, 1);
-      __threadfence_system();
+      raise_link_error(link_error, 1);
       return false;
     }
   }
@@ -115,7 +124,7 @@ struct SlabLinkDev {
   unsigned* my_words;     // my control words, written by the neighbours
   unsigned *send_seq, *recv_seq, *ticket;  // private counters, advanced by the kernels
   unsigned *range_seq, *step_seq, *push_ticket;
-  int* link_error;        // mapped host word, raised when a wait gave up (sticky: later waits return at once)
+  int* link_error;        // device word, raised when a wait gave up (sticky: later waits return at once; see raise_link_error)
   size_t stage_elems;     // floats per receive buffer: halo * W * 3
 };
 
@@ -170,7 +179,13 @@ struct Sim {
   int force_variant;      // -1 = any tile variant
   int plan_variant, plan_T;  // tile plan of the last projection (projection_pack.cu)
   static constexpr int kMaxPlans = 8;
-  struct Plan { int iterations, variant, T, push; } plans[kMaxPlans];  // one per iteration count seen
+  struct Plan { int iterations, variant, T, push, resident, resident_ok; } plans[kMaxPlans];  // one per iteration count seen
+  // resident projection (projection_pack.cu, ResidentArgs): the whole projection in one cooperative launch
+  int resident;            // option (default 1): consider resident plans when the tiles fit on the GPU at once
+  int plan_resident;       // the plan of the last projection is a resident one
+  unsigned* d_resident;    // [0] epoch the exchange tags count from, [1] ticket of finished tiles
+  void* d_box;             // the four mailbox arrays of the ring exchange (8 bytes per cell each), allocated on demand
+  int *h_resident_error, *d_resident_error;  // mapped host word raised by a tile whose neighbour never showed up
   int n_plans;
   char plan_log[2048];     // candidates of the last tuning (sayal_plan_log)
   // issue order of the tiles (most expensive first) per tile geometry, built on first use (projection_pack.cu)
@@ -191,7 +206,7 @@ struct Sim {
   void* link_block;         // neighbour-writable block (control words + receive areas), IPC-exportable
   unsigned* link_counters;  // private
   SlabLinkDev link;
-  int* h_link_error;        // host view of link.link_error (cudaHostAlloc, mapped): read after a sync at no cost
+  int* h_link_error;        // mapped host mirror of link.link_error, written by the kernel that raises it: read after a sync at no cost
   void* ipc_opened[2];      // peer link blocks opened with cudaIpcOpenMemHandle (closed on destroy)
   void* ipc_opened_vel[2];  // peer velocity blocks, likewise
   // in-pass push (projection_pack.cu): the neighbours' four velocity arrays as addressable from this device, in

@@ -17,7 +17,7 @@
 // replayed.  The receive area is double-buffered by sequence parity; a buffer is reused two exchanges later,
 // and by then this rank has consumed the neighbour's next push, which the neighbour issued (stream order) after
 // it had unpacked the earlier one — so no acknowledgement is needed.  A spin that lasts longer than ~2 s gives
-// up, raises the sim's sticky `link_error` word (mapped host memory) and skips the unpack instead of hanging the
+// up, raises the sim's sticky `link_error` word (device memory, mirrored once into mapped host memory) and skips the unpack instead of hanging the
 // GPU or consuming a stale buffer; sayal_sync / sayal_run / sayal_get_field then return SAYAL_ELINK.
 //
 // The same block carries two more neighbour-to-neighbour messages: the pass flags of projection passes that push
@@ -121,8 +121,7 @@ __global__ void __launch_bounds__(XTHREADS) slab_exchange_kernel(Grid g, int hal
       const long long t0 = now_ns();
       while ((int)(ld_acquire_sys(d.my_words + LW_XFLAG + side) - (seq + 1)) < 0) {
         if (now_ns() - t0 > kSpinLimitNs || *reinterpret_cast<volatile int*>(d.link_error) != 0) {
-          atomicCAS(d.link_error, LINK_OK, LINK_TIMEOUT);  // neighbour gone: do not hang the GPU
-          __threadfence_system();
+          raise_link_error(d.link_error, LINK_TIMEOUT);  // neighbour gone: do not hang the GPU
           ok = 0;
           break;
         }
@@ -195,7 +194,7 @@ __global__ void slab_push_wait_kernel(SlabLinkDev d, int passes, int signature) 
   if (side < 2 && d.peer_words[side] && *reinterpret_cast<volatile int*>(d.link_error) == 0) {
     const unsigned target = (*d.step_seq << 10) + (unsigned)passes;
     if (spin_until(d.my_words + LW_PFLAG + side, target, d.link_error)) {
-      if ((int)__ldcg(d.my_words + LW_PITER + side) != signature) atomicCAS(d.link_error, LINK_OK, LINK_PLAN_MISMATCH);
+      if ((int)__ldcg(d.my_words + LW_PITER + side) != signature) raise_link_error(d.link_error, LINK_PLAN_MISMATCH);
     }
   }
   __syncthreads();
@@ -238,7 +237,10 @@ int slab_link_alloc(Sim* s) {
   d.range_seq = s->link_counters + 8;
   d.step_seq = s->link_counters + 9;
   d.push_ticket = s->link_counters + 10;  // [2]
-  d.link_error = d_err;
+  // device word + the address of its host mirror (raise_link_error)
+  d.link_error = reinterpret_cast<int*>(s->link_counters + 12);
+  e = cudaMemcpy(s->link_counters + 14, &d_err, sizeof d_err, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return set_error(SAYAL_ECUDA, cudaGetErrorString(e));
   d.peer_recv[0] = d.peer_recv[1] = nullptr;
   d.peer_words[0] = d.peer_words[1] = nullptr;
   return SAYAL_OK;

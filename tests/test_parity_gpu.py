@@ -108,6 +108,62 @@ def test_tiled_projection_any_temporal_block(T, rows, kernel):
     assert_same(gpu, cpu, names=("u", "v"), what=f"tiled T={T}")
 
 
+@pytest.mark.parametrize("rows", [8, 10, 12])
+@pytest.mark.parametrize("T", [1, 2, 3, 5, 8])
+def test_resident_projection_any_block(T, rows):
+    """Resident plans (the whole projection in one cooperative launch, tiles kept in registers, ring exchange between
+    sweep blocks of T iterations) must give the bits of the plain half-sweeps: several tiles in x and y, n not divisible
+    by T (uneven blocks), every tile variant, both exchange parities (odd and even numbers of blocks)."""
+    cfg = baseline_config(1, width=520, height=470)
+    for n in (13, 14):
+        gpu, cpu = pair(cfg)
+        gpu.set_option("resident", 2)  # resident plans only
+        gpu.set_option("temporal_block", T)
+        gpu.set_option("tile_rows_per_warp", rows)
+        gpu.stage_projection(n, 0.05)
+        assert gpu.get_option("plan_resident") == 1
+        gpu.stage_projection(n, 0.05)  # a second launch: the epoch of the progress words moves on
+        cpu.projection(n, 0.05)
+        cpu.projection(n, 0.05)
+        assert_same(gpu, cpu, names=("u", "v"), what=f"resident T={T} rows={rows} n={n}")
+        gpu.close()
+
+
+@pytest.mark.parametrize("graph", [0, 1])
+def test_resident_full_steps_bit_exact(graph):
+    """Whole steps with the resident projection (forces folded into its load, extrapolation into its store), eager and
+    as graph replays, against the oracle."""
+    cfg = baseline_config(1, width=640, height=360)
+    cfg["sim.projection.n"] = 11
+    gpu, cpu = pair(cfg)
+    gpu.set_option("resident", 2)
+    gpu.set_option("use_graph", graph)
+    gpu.run(3)
+    assert gpu.get_option("plan_resident") == 1
+    for _ in range(3):
+        cpu.step(None, cfg.c.d_t)
+    assert_same(gpu, cpu, what=f"resident steps graph={graph}")
+
+
+def test_resident_full_size_equals_tiled_passes():
+    """BASELINE configs[1] (1920x1080, n = 50): the resident plan the tuner may choose gives the bits of the multi-pass
+    tiled plan over three whole steps."""
+    cfg = baseline_config(1)
+    u, v, sm = synthetic_fields(cfg.c.width, cfg.c.height)
+    out = []
+    for resident in (0, 2):
+        f = Fluid(cfg)
+        for name, a in (("u", u), ("v", v), ("smoke", sm)):
+            f.set_field(name, a)
+        f.set_option("resident", resident)
+        f.run(3)
+        assert f.get_option("plan_resident") == (1 if resident else 0)
+        out.append({n: f.get_field(n) for n in ("u", "v", "smoke")})
+        f.close()
+    for n in ("u", "v", "smoke"):
+        assert np.array_equal(out[0][n].view(np.uint32), out[1][n].view(np.uint32)), n
+
+
 def test_projection_with_pressure_and_range():
     cfg = baseline_config(0)
     gpu, cpu = pair(cfg)

@@ -174,6 +174,33 @@ def test_native_slabs_report_a_too_small_margin():
     assert errors == 0 and overflow > 0
 
 
+def test_silent_neighbour_raises_a_sticky_link_error():
+    """A linked slab whose neighbour never steps: the waits give up after 2 s, nothing is unpacked, and every later
+    synchronising call reports SAYAL_ELINK instead of handing out fields (no silent corruption)."""
+    from opensayal_b200 import SayalError
+    from opensayal_b200._abi import SAYAL_ELINK
+    cfg = baseline_config(1, width=256, height=256)
+    cfg["sim.projection.n"] = 4
+    sims = []
+    for r in range(2):
+        row0, rows = S.slab_rows(cfg.c.height, 2, r)
+        sims.append(Fluid(cfg, device=0, slab=(row0, rows, 18)))
+    S.link_local(sims)
+    for f in sims:
+        f.run(0)
+    sims[0].step_async(None)  # sims[1] stays silent
+    with pytest.raises(SayalError) as e:
+        sims[0].sync()
+    assert e.value.code == SAYAL_ELINK
+    assert sims[0].get_option("link_error") != 0
+    with pytest.raises(SayalError):
+        sims[0].get_field("u")
+    with pytest.raises(SayalError):
+        sims[0].step_async(None)
+    for f in sims:
+        f.close()
+
+
 def test_unlinked_slab_refuses_to_step():
     from opensayal_b200 import SayalError
     cfg = baseline_config(1, width=256, height=256)
