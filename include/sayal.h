@@ -304,7 +304,7 @@ int sayal_slab_unpack_ghost(sayal_sim* sim, int32_t side, int32_t nrows, int32_t
  *   push mode (default; option "slab_push"): every projection pass sweeps the owned rows plus 2 x its iterations of
  *     ghost rows, and the tiles that produce the slab's edge rows store them a second time straight into the
  *     neighbour's ghost rows and publish a flag the neighbour's next pass waits on — compute and exchange are one
- *     kernel, a step needs halo >= max(2 T, advect_margin + 2) ghost rows (T = iterations per pass, at most 8);
+ *     kernel, a step needs halo >= max(2 T, advect_margin + 2) ghost rows (T = iterations per pass, at most 10);
  *   otherwise: ghost rows lose two rows of validity per SOR iteration and are refreshed by an exchange kernel only
  *     when the next operation needs more depth than is left (halo >= 2 n + advect_margin + 2: never inside a step).
  * Either way one exchange at the end of the step carries u, v (halo rows) and smoke (advect_margin + 2 rows), hidden

@@ -31,6 +31,7 @@
 // Roofline: HBM.  Algorithmic bytes are 17 B per cell per iteration (r/w u, v + 1 flag byte); one pass moves
 // (1 + halo overhead) * 9 B in and 8 B out per cell for T iterations.
 #include <cstdio>
+#include <cstdlib>
 
 #include "sayal_internal.h"
 
@@ -140,6 +141,8 @@ struct PushArgs {
   int on;                    // bit d: a neighbour on side d (0 = low memory rows) takes this pass's edge rows
   int pass_index;            // 0: the ghost rows came with the end-of-step exchange (stream order), nothing to wait for
   int signature;             // (iterations << 8) | passes of the step's plan: both sides must agree
+  int debug;                 // profiling only (SAYAL_DEBUG_PUSH; results are wrong): 1 = no peer stores, 2 = no system
+                             // fence before the ticket, 4 = no wait for the neighbour's flag
   int src_lo[2], src_hi[2];  // my local rows that travel to side d
   int dst_row0[2];           // row of src_lo[d] in the neighbour's arrays
   int n_pushers[2];          // tiles whose written rows meet [src_lo, src_hi): the last one publishes the flag
@@ -440,7 +443,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
     const unsigned target = (*a.push.step_seq << 10) + (unsigned)a.push.pass_index;
     const bool need0 = (a.push.on & 1) && (lr0 - (w == 0 ? 1 : 0) < a.write_lo || (w == 0 && push0));
     const bool need1 = (a.push.on & 2) && (lr0 + RY > a.write_hi || (w == 0 && push1));
-    if (need0 || need1) {
+    if ((need0 || need1) && !(a.push.debug & 4)) {
       if (lane == 0) {
         if (need0) spin_until(a.push.my_words + LW_PFLAG + 0, target, a.push.link_error);
         if (need1) spin_until(a.push.my_words + LW_PFLAG + 1, target, a.push.link_error);
@@ -829,6 +832,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
           u64 q02 = lds64(sp_warp + r * 128), q13 = lds64(sp_warp + r * 128 + 64);
           *reinterpret_cast<float4*>(a.p + k) = make_float4(lo(q02), lo(q13), hi(q02), hi(q13));
         }
+        if (a.push.debug & 1) continue;
         if (push0 && lr >= a.push.src_lo[0] && lr < a.push.src_hi[0]) {  // my edge rows = the neighbour's ghost rows
           size_t kp = (size_t)(lr - a.push.src_lo[0] + a.push.dst_row0[0]) * g.pitch + x;
           *reinterpret_cast<float4*>(a.push.peer_u[0] + kp) = uo;
@@ -845,7 +849,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   if (push0 || push1) {  // uniform over the CTA
     __syncthreads();     // every thread's stores are issued before thread 0 fences at system scope
     if (threadIdx.x == 0) {
-      __threadfence_system();
+      if (!(a.push.debug & 2)) __threadfence_system();
       const unsigned published = (*a.push.step_seq << 10) + (unsigned)a.push.pass_index + 1u;
 #pragma unroll
       for (int d = 0; d < 2; d++) {
@@ -936,6 +940,7 @@ struct Variant {
 const Variant kVariants[] = {SAYAL_PACK_VARIANT(8, 16), SAYAL_PACK_VARIANT(10, 16), SAYAL_PACK_VARIANT(12, 16)};
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kMaxT = 16;
+constexpr int kMaxPushT = 10;  // push mode: iterations per pass at most (the halo allowing)
 
 int tiles_for(int extent, int tile, int stride) {
   if (extent <= tile) return 1;
@@ -1244,6 +1249,10 @@ int run_passes(Sim* s, int variant, int T, int iterations, float d_t, bool with_
     if (push_sides) {
       PushArgs& pu = a.push;
       pu.on = push_sides;
+      {
+        static const int dbg = getenv("SAYAL_DEBUG_PUSH") ? atoi(getenv("SAYAL_DEBUG_PUSH")) : 0;
+        pu.debug = dbg;
+      }
       pu.pass_index = pass;
       pu.signature = signature;
       // the neighbour's output arrays of this pass: it ping-pongs in step with us, so its output is the array with
@@ -1520,9 +1529,9 @@ int launch_projection_tiled(Sim* s, int iterations, float d_t) {
 
 // Push mode: the temporal block every rank of a chain uses for `iterations` iterations with `halo` ghost rows.  It
 // must not depend on anything rank-local (neighbours pair their passes one to one), so it is a function of these
-// two numbers only: the even split of `iterations` into passes of at most min(halo / 2, 8) iterations.
+// two numbers only: the even split of `iterations` into passes of at most min(halo / 2, 10) iterations.
 int tiled_push_temporal_block(int iterations, int halo) {
-  int cap = halo / 2 < 8 ? halo / 2 : 8;
+  int cap = halo / 2 < kMaxPushT ? halo / 2 : kMaxPushT;
   if (cap < 1 || iterations <= 0) return 0;
   const int passes = (iterations + cap - 1) / cap;
   return (iterations + passes - 1) / passes;

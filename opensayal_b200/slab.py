@@ -596,9 +596,12 @@ def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSa
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     warm = max(args.warmup, 3)
 
+    no_flush = bool(os.environ.get("SAYAL_BENCH_NO_FLUSH"))  # experiments only: the L2-warm step, same harness
+
     def one_step(a=None, b=None):
-        with torch.cuda.stream(stream):
-            flush.fill_(1)
+        if not no_flush:
+            with torch.cuda.stream(stream):
+                flush.fill_(1)
         if a is not None:
             a.record(stream)
         sf.run(1)

@@ -128,6 +128,92 @@ def test_one_step_error_full_size_1920x1080():
         assert rel_l2(g, r) <= TOL, n
 
 
+def _one_step_vs_reference(cfg, fields_from_gpu=False):
+    """One step of the reference build and of the CUDA path from identical fields: masks memcmp-equal, rel-L2 <= TOL
+    outside the H4 windows (whose cell count is returned with the errors).  Large grids take their fields from the
+    torch generator of slab.device_fields (the numpy one would take longer than the test)."""
+    import gc
+    H, W = cfg.c.height, cfg.c.width
+    ref, gpu = RefSim(cfg.c), Fluid(cfg)
+    for field in ("is_solid", "total_s"):
+        a, b = ref.get_field(field), gpu.get_field(field)
+        assert a.dtype == b.dtype and np.array_equal(a, b), field  # int32 words: equal values are equal bytes
+        del a, b
+    if fields_from_gpu:
+        import torch
+        from opensayal_b200.slab import device_fields
+        u, v, sm = (t.cpu().numpy() for t in device_fields(W, H, (0, H), torch.device("cuda", 0)))
+        torch.cuda.empty_cache()
+    else:
+        u, v, sm = synthetic_fields(W, H)
+    for sim in (ref, gpu):
+        for n, a in (("u", u), ("v", v), ("smoke", sm)):
+            sim.set_field(n, a)
+    del u, v, sm
+    gc.collect()
+    ref.step(None)
+    gpu.update(None)
+    errors, excluded = {}, 0
+    for n in ("u", "v", "smoke"):
+        r, g = ref.get_field(n), gpu.get_field(n)
+        excluded = exclude_contested((r, g), H, W)
+        errors[n] = rel_l2(g, r)
+        del r, g
+        gc.collect()
+    ref.close()
+    gpu.close()
+    print(f"{W}x{H} n={cfg.c.proj_n}: one-step rel-L2 vs reference {errors}; H4 windows exclude {excluded} of {W * H} cells")
+    for n, e in errors.items():
+        assert e <= TOL, f"{n}: {e:.3e}"
+    return errors, excluded
+
+
+def test_one_step_error_3840x2160_n100_decay():
+    """BASELINE configs[2]: 3840 x 2160 wind tunnel + disc + smoke decay 0.05, n = 100."""
+    _one_step_vs_reference(baseline_config(2))
+
+
+def test_one_step_error_16384x16384():
+    """BASELINE configs[3] on one GPU through the whole-domain path: 16384 x 16384, n = 50 (the reference build holds
+    9 GiB, ours 8.3 GiB)."""
+    _one_step_vs_reference(baseline_config(3), fields_from_gpu=True)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_drift_1000_steps_vs_reference(name):
+    """north_star: "drift reported over 1000 steps" — BASELINE configs[0] (256 x 144 tank, 1000 steps) and the
+    480 x 270 wind tunnel, free-running from the synthetic fields; rel-L2 of every field at steps 1, 10, 100, 1000 goes
+    to the test log and to gpurun_out/drift_<name>.json (copied to profiles/ by hand).  Gated: step 1 meets the
+    one-step tolerance, everything stays finite.  The flow is chaotic (wake, sloshing): growth is expected."""
+    import json
+    import os
+    cfg = CASES[name]()
+    H, W = cfg.c.height, cfg.c.width
+    ref, gpu = RefSim(cfg.c), Fluid(cfg)
+    load_all((ref, gpu), cfg)
+    names = ("u", "v", "smoke") + (("p",) if cfg.c.enable_pressure else ())
+    drift, excluded = {}, 0
+    for step in range(1, 1001):
+        ref.step(None)
+        gpu.update(None)
+        if step in (1, 10, 100, 1000):
+            drift[step] = {}
+            for n in names:
+                g, r = gpu.get_field(n), ref.get_field(n)
+                if step == 1:
+                    excluded = exclude_contested((g, r), H, W)
+                drift[step][n] = rel_l2(g, r)
+    record = {"config": name, "grid": [W, H], "sor_iterations": cfg.c.proj_n, "steps": 1000, "rel_l2_vs_reference_build": drift,
+              "h4_cells_excluded_at_step_1": excluded, "cells": W * H,
+              "note": "CUDA path (IEEE) vs the reference's own CUDA build (--use_fast_math), free-running from identical fields"}
+    print("drift vs reference:", json.dumps(record))
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/drift_{name}.json", "w") as f:
+        json.dump(record, f, indent=1)
+    assert all(e <= TOL for e in drift[1].values())
+    assert all(np.isfinite(list(d.values())).all() for d in drift.values())
+
+
 def test_drift_report_vs_reference():
     """Free-run both; report rel-L2 at steps 1, 10, 100 (chaotic wake => growth expected; not gated beyond
     sanity: the first step must meet the tolerance and nothing may blow up)."""
