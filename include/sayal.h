@@ -258,6 +258,11 @@ int sayal_plan_log(sayal_sim* sim, char* buf, int32_t capacity);
 /* Profiling only (option "debug_timeline" = 1): per-CTA timestamps of the last projection pass, 5 int64 per tile
  * {entry, tile loaded, sweeps done, stores issued (globaltimer ns), SM id}. */
 int sayal_debug_timeline(sayal_sim* sim, int64_t* host_dst, int32_t max_tiles, int32_t* n_tiles);
+/* Profiling only (option "debug_events" = 1, eager sayal_step): milliseconds from the start of the last step to its
+ * stage boundaries — [1] projection done, [2] velocity advected, [3] / [4] edge rows of the velocity / smoke advected
+ * (linked slabs), [5] end-of-step exchange done (aux stream), [6] interior rows advected, [7] step done; -1 = not
+ * reached in that step. */
+int sayal_debug_stage_times(sayal_sim* sim, float* ms_out, int32_t capacity);
 /* Diagnostics of a slab link: the 64 neighbour-written control words of this sim followed by its 32 private counters
  * (layout: csrc/sayal_internal.h), copied after the sim's stream has drained. */
 int sayal_debug_link_words(sayal_sim* sim, uint32_t* host_dst /* 96 words */);
@@ -304,7 +309,7 @@ int sayal_slab_unpack_ghost(sayal_sim* sim, int32_t side, int32_t nrows, int32_t
  *   push mode (default; option "slab_push"): every projection pass sweeps the owned rows plus 2 x its iterations of
  *     ghost rows, and the tiles that produce the slab's edge rows store them a second time straight into the
  *     neighbour's ghost rows and publish a flag the neighbour's next pass waits on — compute and exchange are one
- *     kernel, a step needs halo >= max(2 T, advect_margin + 2) ghost rows (T = iterations per pass, at most 10);
+ *     kernel, a step needs halo >= max(2 T, advect_margin + 2) ghost rows (T = iterations per pass, at most 8);
  *   otherwise: ghost rows lose two rows of validity per SOR iteration and are refreshed by an exchange kernel only
  *     when the next operation needs more depth than is left (halo >= 2 n + advect_margin + 2: never inside a step).
  * Either way one exchange at the end of the step carries u, v (halo rows) and smoke (advect_margin + 2 rows), hidden

@@ -940,7 +940,7 @@ struct Variant {
 const Variant kVariants[] = {SAYAL_PACK_VARIANT(8, 16), SAYAL_PACK_VARIANT(10, 16), SAYAL_PACK_VARIANT(12, 16)};
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kMaxT = 16;
-constexpr int kMaxPushT = 10;  // push mode: iterations per pass at most (the halo allowing)
+constexpr int kMaxPushT = 8;   // push mode: iterations per pass at most (the halo allowing)
 
 int tiles_for(int extent, int tile, int stride) {
   if (extent <= tile) return 1;
@@ -1529,7 +1529,7 @@ int launch_projection_tiled(Sim* s, int iterations, float d_t) {
 
 // Push mode: the temporal block every rank of a chain uses for `iterations` iterations with `halo` ghost rows.  It
 // must not depend on anything rank-local (neighbours pair their passes one to one), so it is a function of these
-// two numbers only: the even split of `iterations` into passes of at most min(halo / 2, 10) iterations.
+// two numbers only: the even split of `iterations` into passes of at most min(halo / 2, 8) iterations.
 int tiled_push_temporal_block(int iterations, int halo) {
   int cap = halo / 2 < kMaxPushT ? halo / 2 : kMaxPushT;
   if (cap < 1 || iterations <= 0) return 0;

@@ -92,6 +92,8 @@ static void free_sim(Sim* s) {
     if (s->ev_copied[k]) cudaEventDestroy(s->ev_copied[k]);
   }
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+  for (int k = 0; k < Sim::kDbgEvents; k++)
+    if (s->dbg_ev[k]) cudaEventDestroy(s->dbg_ev[k]);
   if (s->ev_fork) cudaEventDestroy(s->ev_fork);
   if (s->ev_join) cudaEventDestroy(s->ev_join);
   if (s->aux_stream) cudaStreamDestroy(s->aux_stream);
@@ -286,6 +288,17 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   return SAYAL_OK;
 }
 
+// profiling only: stage boundary `k` of the running step, on `stream` (nothing while a graph is being captured)
+static void dbg_mark(Sim* s, int k, cudaStream_t stream) {
+  if (!s->debug_events || k < 0 || k >= Sim::kDbgEvents) return;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s->stream, &cap);
+  if (cap != cudaStreamCaptureStatusNone) return;
+  if (!s->dbg_ev[k] && cudaEventCreate(&s->dbg_ev[k]) != cudaSuccess) return;
+  cudaEventRecord(s->dbg_ev[k], stream);
+  s->dbg_marked |= 1u << k;
+}
+
 static void swap_ptr(float*& a, float*& b) {
   float* t = a;
   a = b;
@@ -359,6 +372,7 @@ static int advect_linked(Sim* s, float d_t, bool smoke, int ghost, int exchange_
     TRY(advect_rows(s, d_t, smoke, g.own_hi - halo, hi));
     CUDA_TRY(cudaEventRecord(s->ev_fork, s->stream));
     CUDA_TRY(cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0));
+    dbg_mark(s, smoke ? 4 : 3, s->stream);  // edge rows advected
     // The exchange is enqueued BEFORE the interior rows: its few fat CTAs must find room while the SMs are empty
     // (behind a grid of thousands of small blocks they would only be placed when that grid drains, i.e. the
     // exchange would run after the advection instead of under it).  It reads the edge rows the two kernels above
@@ -368,8 +382,10 @@ static int advect_linked(Sim* s, float d_t, bool smoke, int ghost, int exchange_
     swap_fields();  // ... the interior kernel the old ones
     if (r != SAYAL_OK) return r;
     CUDA_TRY(cudaEventRecord(s->ev_join, s->aux_stream));
+    dbg_mark(s, 5, s->aux_stream);  // exchange done
     TRY(advect_rows(s, d_t, smoke, g.own_lo + halo, g.own_hi - halo));
     swap_fields();
+    dbg_mark(s, 6, s->stream);  // interior rows advected
     CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
   } else {
     TRY(advect_rows(s, d_t, smoke, lo, hi));
@@ -385,6 +401,8 @@ bool push_mode(const Sim* s);
 static int step_impl(Sim* s, const sayal_source* src, float d_t) {
   const bool linked = is_linked(s);
   const int skip = s->debug_skip;  // profiling only: marginal cost of a stage inside the replayed graph
+  s->dbg_marked = 0;
+  dbg_mark(s, 0, s->stream);
   if (!(skip & 1)) TRY(launch_forces(s, src, d_t, true));  // may defer to the first projection pass (fuse_forces)
   if (s->ph.enable_pressure) TRY(launch_zero_pressure(s));
   // apply_diffusion (fluid.cu:775-777): n sweeps over u when viscosity != 0, in a fixed red-black order (H1).
@@ -437,6 +455,7 @@ static int step_impl(Sim* s, const sayal_source* src, float d_t) {
       done += k;
     }
   }
+  dbg_mark(s, 1, s->stream);  // projection done
   bool range_forked = false;
   if (s->ph.enable_pressure) {
     TRY(launch_pressure_range(s));
@@ -464,6 +483,7 @@ static int step_impl(Sim* s, const sayal_source* src, float d_t) {
     }
     set_valid_depth(s, D);
     int r = (skip & 4) ? SAYAL_OK : advect_linked(s, d_t, false, 1, smoke ? 0 : end_mask);
+    dbg_mark(s, 2, s->stream);  // velocity advected
     if (r == SAYAL_OK && smoke) {
       // new velocity: exact on the owned rows +- 1; smoke ghosts: exact as deep as exchanges carry smoke
       // (advect_margin + 2 rows, slab_exchange.cu) — a gather beyond that counts as halo overflow
@@ -476,6 +496,7 @@ static int step_impl(Sim* s, const sayal_source* src, float d_t) {
     if (r != SAYAL_OK) return r;
   }
   if (range_forked) CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_range, 0));
+  dbg_mark(s, 7, s->stream);  // step done
   return SAYAL_OK;
 }
 
@@ -1016,6 +1037,8 @@ int sayal_set_option(sayal_sim* sim, const char* key, int64_t value) {
     s->fuse_extrapolation = value != 0;
   } else if (!strcmp(key, "shrink_window")) {
     s->shrink_window = value != 0;
+  } else if (!strcmp(key, "debug_events")) {
+    s->debug_events = value != 0;
   } else if (!strcmp(key, "resident")) {
     if (value < 0 || value > 2) return set_error(SAYAL_EINVAL, "resident must be 0 (off), 1 (candidate) or 2 (resident plans only)");
     s->resident = (int)value;
@@ -1117,6 +1140,20 @@ int sayal_stream_delay(sayal_sim* sim, int64_t microseconds) {
   CUDA_TRY(cudaSetDevice(s->device));
   stream_delay_kernel<<<1, 1, 0, s->stream>>>(microseconds * 1000);
   CUDA_TRY(cudaGetLastError());
+  return SAYAL_OK;
+}
+
+int sayal_debug_stage_times(sayal_sim* sim, float* ms_out, int32_t capacity) {
+  if (!sim || !ms_out) return set_error(SAYAL_EINVAL, "sayal_debug_stage_times: null argument");
+  Sim* s = S(sim);
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if (s->aux_stream) CUDA_TRY(cudaStreamSynchronize(s->aux_stream));
+  for (int k = 0; k < capacity; k++) {
+    ms_out[k] = -1.f;
+    if (k < Sim::kDbgEvents && (s->dbg_marked & 1u) && (s->dbg_marked & (1u << k)))
+      if (cudaEventElapsedTime(&ms_out[k], s->dbg_ev[0], s->dbg_ev[k]) != cudaSuccess) { cudaGetLastError(); ms_out[k] = -1.f; }
+  }
   return SAYAL_OK;
 }
 

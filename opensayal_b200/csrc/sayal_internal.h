@@ -173,6 +173,11 @@ struct Sim {
   ForceArgs fuse_args;
   int shrink_window;      // option: linked slabs sweep only the ghost rows that are still exact (default 1)
   int proj_depth;         // linked slabs: ghost rows still exact when the next projection call starts (-1: all rows)
+  // profiling only (option "debug_events", eager steps): CUDA events at the stage boundaries of the last step
+  static constexpr int kDbgEvents = 10;
+  cudaEvent_t dbg_ev[kDbgEvents];
+  int debug_events;
+  unsigned dbg_marked;    // bit k: dbg_ev[k] was recorded in the last step
   int debug_skip;         // profiling only (option "debug_skip"): bit mask of step stages to leave out (wrong results!)
   int fuse_extrap;        // 1: the next tiled projection call ends the step's projection and also extrapolates; 2: it did
   int autotune;           // time candidate tile plans on first use

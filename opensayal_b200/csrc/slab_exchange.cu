@@ -23,6 +23,7 @@
 // The same block carries two more neighbour-to-neighbour messages: the pass flags of projection passes that push
 // their edge rows themselves (projection_pack.cu) and the chain reduction of the pressure range.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "sayal_internal.h"
@@ -320,7 +321,8 @@ int launch_slab_exchange_on(Sim* s, int field_mask, cudaStream_t stream) {
   // at most 8 fat CTAs per side: the exchange shares the GPU with the interior tiles it overlaps with, and the
   // waiting CTAs of one slab must never fill the device, or a second slab on the same device (tests) could not
   // run the kernels the wait is waiting for
-  if (blocks > 8) blocks = 8;
+  static const int max_blocks = getenv("SAYAL_XCHG_BLOCKS") ? atoi(getenv("SAYAL_XCHG_BLOCKS")) : 8;  // experiments
+  if (blocks > max_blocks) blocks = max_blocks;
   slab_exchange_kernel<<<dim3(blocks, 2), XTHREADS, 0, stream>>>(s->g, s->slab_halo, fs, d);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(SAYAL_ECUDA, cudaGetErrorString(e));

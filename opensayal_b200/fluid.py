@@ -352,6 +352,12 @@ class Fluid:
         check(self._lib.sayal_debug_timeline(self._sim, out.ctypes.data_as(C.c_void_p), max_tiles, C.byref(n)))
         return out[: n.value]
 
+    def debug_stage_times(self) -> np.ndarray:
+        """Profiling only (option debug_events): ms from the start of the last eager step to its stage boundaries."""
+        out = np.zeros(10, dtype=np.float32)
+        check(self._lib.sayal_debug_stage_times(self._sim, out.ctypes.data_as(C.c_void_p), 10))
+        return out
+
     def debug_link_words(self) -> np.ndarray:
         """Diagnostics: 64 control words of the slab link + 32 private counters (csrc/sayal_internal.h)."""
         out = np.zeros(96, dtype=np.uint32)

@@ -31,13 +31,25 @@ slabs on one GPU (tests) and a numpy stand-in under gloo on CPU (tests of the ho
 """
 from __future__ import annotations
 
+import os
+
 from typing import Callable, List, Optional, Sequence, Tuple
 
 F_U, F_V, F_SMOKE, F_P = 1, 2, 4, 8
 
 
-def slab_rows(height: int, world: int, rank: int) -> Tuple[int, int]:
-    """(row0, rows) of rank's slab: contiguous memory rows, remainder spread over the first ranks."""
+def slab_rows(height: int, world: int, rank: int, edge_bonus: int = 0) -> Tuple[int, int]:
+    """(row0, rows) of rank's slab: contiguous memory rows, remainder spread over the first ranks.
+    edge_bonus > 0 (deep-halo schedule, world > 2): the two edge slabs own that many rows more than the interior ones —
+    they sweep ghost rows on one side only, the interior slabs on two, so equal ownership leaves the edge GPUs waiting
+    at the end-of-step exchange."""
+    if edge_bonus > 0 and world > 2:
+        interior = (height - 2 * edge_bonus) // world
+        edge = interior + edge_bonus
+        sizes = [edge] + [interior] * (world - 2) + [edge]
+        for k in range(height - sum(sizes)):  # remainder: one row each, from the first rank on
+            sizes[k % world] += 1
+        return sum(sizes[:rank]), sizes[rank]
     base, extra = divmod(height, world)
     rows = base + (1 if rank < extra else 0)
     row0 = rank * base + min(rank, extra)
@@ -324,6 +336,23 @@ def link_dist(sim, rank: int, world: int, group=None) -> None:
     dist.barrier(group=group)
 
 
+def choose_slab_schedule(width: int, rows_per_slab: int, n_iterations: int, world: int, margin: int = 16):
+    """("push" | "deep", halo) for linked slabs of `rows_per_slab` owned rows — a function of numbers every rank knows,
+    so all ranks choose alike.  Deep halo (2 n + margin + 2 ghost rows, recomputed, one exchange per step) costs the
+    projection time x the share of ghost rows swept (they shrink by two rows per iteration: half the halo on average,
+    plus a tile row's worth of quantisation); push mode (thin halo, every pass stores its edge rows into the
+    neighbour) costs a fixed ~35 us per step on a B200 (measured, profiles/README.md: system fences of the pushing
+    tiles, pass flags, the wait kernel).  Thin slabs of a small grid take the deep halo, everything else pushes."""
+    deep_halo = 2 * n_iterations + margin + 2
+    push_halo = max(margin + 2, 16)
+    if rows_per_slab < 4 * deep_halo:  # the deep schedule hides its exchange under interior rows: needs room
+        return "push", push_halo
+    projection_us = rows_per_slab * width * n_iterations * 1.3e-6
+    sides = 2 if world > 2 else 1
+    deep_extra = projection_us * sides * (deep_halo / 2 + 10) / rows_per_slab
+    return ("deep", deep_halo) if deep_extra < 35.0 else ("push", push_halo)
+
+
 class SlabFluid:
     """`Fluid` over N y-slabs, one process per slab (torch.distributed must be initialised).
 
@@ -332,13 +361,19 @@ class SlabFluid:
     transport "nccl": the same schedule driven from here, edge rows packed and sent with NCCL send/recv."""
 
     def __init__(self, cfg, rank: int, world: int, device: int, halo: Optional[int] = None, group=None,
-                 transport: str = "p2p", margin: int = 16):
+                 transport: str = "p2p", margin: int = 16, push: Optional[bool] = None, balance: bool = False):
         self.cfg, self.rank, self.world, self.group = cfg, rank, world, group
         self.transport = transport if world > 1 else "none"
         c = cfg.c
-        if halo is None:  # enough for a step in push mode: 2 T <= 16 rows per pass, margin + 2 rows for the advection
-            halo = max(margin + 2, 16)
-        row0, rows = slab_rows(c.height, world, rank)
+        if halo is None:  # thin halo + pushing passes, or deep halo + one exchange per step (choose_slab_schedule)
+            mode, halo = choose_slab_schedule(c.width, c.height // max(world, 1), c.proj_n, world, margin)
+            if push is None:
+                push = mode == "push"
+        self.push = push  # None: the library's default (push whenever the halo allows)
+        # deep halo: an interior slab sweeps about halo / 2 + 10 ghost rows more than an edge slab (see
+        # choose_slab_schedule); `balance` lets the edge slabs own that many rows more
+        self.edge_bonus = halo // 2 + 10 if (balance and push is False and world > 2) else 0
+        row0, rows = slab_rows(c.height, world, rank, self.edge_bonus)
         if world > 1 and rows < halo:
             raise ValueError(f"slab of {rows} rows is thinner than the halo ({halo})")
         self.row0, self.rows, self.halo = row0, rows, halo
@@ -347,6 +382,8 @@ class SlabFluid:
                                  viscous=c.viscosity != 0) if world > 1 else None
         if self.transport == "p2p":
             self.sim.set_option("advect_margin", margin)  # rows the advection may gather from (see lazy_schedule)
+            if push is not None and not os.environ.get("SAYAL_SLAB_PUSH"):
+                self.sim.set_option("slab_push", 1 if push else 0)
             link_dist(self.sim, rank, world, group)
             self.sim.run(0)  # choose the projection tile plans (may time candidates) before the first exchange
 
@@ -585,11 +622,13 @@ def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSa
     cfg = workload_config(world)
     c = cfg.c
     margin = int(os.environ.get("SAYAL_ADVECT_MARGIN", "16"))
-    # push mode (default): 2 T + margin ghost rows are enough, the projection passes deliver their own edge rows;
-    # SAYAL_SLAB_PUSH=0 + SAYAL_SLAB_HALO=118 measures the deep-halo schedule of round 1
-    halo = int(os.environ.get("SAYAL_SLAB_HALO", "0")) or max(margin + 2, 16)
+    # thin halo + pushing passes or deep halo + one exchange per step: choose_slab_schedule (1080-row slabs of this grid
+    # take the deep halo; the 16384^2 strong-scaling record below pushes).  SAYAL_SLAB_HALO / SAYAL_SLAB_PUSH override.
+    halo = int(os.environ.get("SAYAL_SLAB_HALO", "0")) or None
     transport = os.environ.get("SAYAL_SLAB_TRANSPORT", "p2p")
-    sf = SlabFluid(cfg, rank, world, local, halo=halo, transport=transport, margin=margin)
+    sf = SlabFluid(cfg, rank, world, local, halo=halo, transport=transport, margin=margin,
+                   balance=bool(os.environ.get("SAYAL_SLAB_BALANCE")))  # measured: no effect at 1080 rows per slab
+    halo = sf.halo
     u, v, sm = synthetic_fields(c.width, c.height, rows=(sf.row0, sf.rows))
     sf.set_initial(u, v, sm)
     stream = sf.slab.stream
@@ -696,9 +735,11 @@ def bench_slabs(args, workload_config: Callable, config_block: Callable, ClockSa
             "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_block(cfg, world),
-            "slabs": {"halo_rows": halo, "push_mode": bool(int(plans[0][3])),
-                      "exchange": ("projection passes store their edge rows into the neighbour's ghost rows over NVLink (one kernel "
-                                   "computes and exchanges); end-of-step exchange kernel under the smoke advection; graph-replayed step")
+            "slabs": {"halo_rows": halo, "push_mode": bool(int(plans[0][3])), "edge_slab_bonus_rows": sf.edge_bonus,
+                      "exchange": (("projection passes store their edge rows into the neighbour's ghost rows over NVLink (one kernel "
+                                    "computes and exchanges); " if bool(int(plans[0][3])) else
+                                    "deep halo: ghost rows recomputed through the projection, no exchange inside it; ") +
+                                   "end-of-step exchange kernel (peer-memory stores + flags) under the smoke advection; graph-replayed step")
                       if transport == "p2p" else "NCCL send/recv of packed edge rows",
                       "halo_overflow": int(bad[0]), "link_error": int(bad[1]),
                       "tile_plans_per_rank": [{"temporal_block": int(p[0]), "rows_per_warp": int(p[1]),

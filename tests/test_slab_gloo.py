@@ -356,3 +356,23 @@ def test_gloo_exchange_matches_single_domain(world):
             row0, rows = S.slab_rows(H, world, r)
             for name in ("u", "v", "smoke"):
                 assert np.array_equal(out[r][name], want[name][row0:row0 + rows]), (r, name)
+
+
+def test_slab_schedule_choice_is_a_function_of_shared_numbers():
+    """Thin slabs of a small grid recompute a deep halo (one exchange per step), everything else pushes; every rank
+    derives the same answer from (width, rows per slab, n, world, margin)."""
+    for world in (2, 4, 8):
+        assert S.choose_slab_schedule(1920, 1080, 50, world) == ("deep", 118)      # bench.py --gpus N
+        assert S.choose_slab_schedule(16384, 16384 // world, 50, world) == ("push", 18)  # BASELINE configs[3]
+        assert S.choose_slab_schedule(16384, 8192, 200, world) == ("push", 18)     # BASELINE configs[4]
+    assert S.choose_slab_schedule(1920, 400, 50, 4) == ("push", 18)                # too thin to hide the deep exchange
+    assert S.choose_slab_schedule(1920, 1080, 50, 4, margin=6) == ("deep", 108)
+
+
+def test_slab_rows_with_edge_bonus_partition_the_domain():
+    for height, world, bonus in ((4320, 4, 69), (8640, 8, 69), (1000, 3, 7), (2160, 2, 69), (999, 4, 0)):
+        parts = [S.slab_rows(height, world, r, bonus) for r in range(world)]
+        assert parts[0][0] == 0 and sum(n for _, n in parts) == height
+        assert all(parts[k][0] + parts[k][1] == parts[k + 1][0] for k in range(world - 1))
+        if bonus and world > 2:
+            assert parts[0][1] - parts[1][1] in (bonus, bonus + 1, bonus - 1)

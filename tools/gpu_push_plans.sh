@@ -1,5 +1,5 @@
 #!/bin/bash
-# tools/gpu_push_plans.sh <tag> <N> — weak bench on N GPUs, push mode vs deep halo
+# tools/gpu_push_plans.sh <tag> <N> — weak bench on N GPUs under several slab settings
 set -u
 tag=${1:-r2}; N=${2:-2}
 mkdir -p gpurun_out
@@ -11,13 +11,14 @@ run() {
 import json
 try:
     d=json.load(open("gpurun_out/${tag}_push_${name}_n$N.json"))
-    print("$name", "ms", round(d["ms_per_step"],4), d["step_ms_slowest_rank"], "plans", [(p["temporal_block"],p["rows_per_warp"]) for p in d["slabs"]["tile_plans_per_rank"]][:3], "halo", d["slabs"]["halo_rows"], "push", d["slabs"]["push_mode"], "e2e", round(d["e2e"]["value"]/1e9,2))
+    print("$name", "ms", round(d["ms_per_step"],4), d["step_ms_slowest_rank"]["median"], "plans", [(p["temporal_block"],p["rows_per_warp"]) for p in d["slabs"]["tile_plans_per_rank"]][:3], "halo", d["slabs"]["halo_rows"], "push", d["slabs"]["push_mode"], "e2e", round(d["e2e"]["value"]/1e9,2))
 except Exception as e:
     print("$name failed", e)
 PY
 }
-run push SAYAL_TILE_ROWS=8
-run deep118 SAYAL_SLAB_PUSH=0 SAYAL_SLAB_HALO=118
-run deep118_rows10 SAYAL_SLAB_PUSH=0 SAYAL_SLAB_HALO=118 SAYAL_TILE_ROWS=10
-run deep118_rows12 SAYAL_SLAB_PUSH=0 SAYAL_SLAB_HALO=118 SAYAL_TILE_ROWS=12
-python bench.py --skip-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('single ms', d['ms_per_step'], 'plan', d['plan']['temporal_block'], d['plan']['tile_rows_per_warp'], 'strong1', d['strong_16384'])"
+run auto A=1
+run x4 SAYAL_XCHG_BLOCKS=4
+run x16 SAYAL_XCHG_BLOCKS=16
+run x32 SAYAL_XCHG_BLOCKS=32
+run x64 SAYAL_XCHG_BLOCKS=64
+run nobalance SAYAL_SLAB_NO_BALANCE=1

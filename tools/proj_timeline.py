@@ -31,3 +31,5 @@ print(f"  CTA life: med {np.median(st-ent):6.1f} max {(st-ent).max():6.1f} us")
 order = np.argsort(sw - ld)[::-1][:8]
 tx = None
 print("  slowest sweeps (tile index: us):", [(int(k), round(float((sw-ld)[k]), 1)) for k in order])
+d = np.sort(sw - ld)[::-1]
+print("  sweep time distribution (us), sorted:", [round(float(x), 1) for x in d[:24]], "... median", round(float(np.median(d)), 1))
