@@ -30,8 +30,10 @@
 //
 // Roofline: HBM.  Algorithmic bytes are 17 B per cell per iteration (r/w u, v + 1 flag byte); one pass moves
 // (1 + halo overhead) * 9 B in and 8 B out per cell for T iterations.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "sayal_internal.h"
 
@@ -173,6 +175,17 @@ struct ResidentArgs {
   u64* box_v[2];
 };
 
+// A pass may run over an explicit list of tiles instead of the regular grid (whole domains, no push): the tiles whose
+// warps mostly take the table path (an obstacle's rim) are cut in two along y — each half keeps fewer warps busy and
+// finishes with the open tiles instead of after them (a pass ends when its slowest tile does) — and the last tile row
+// is moved up so that the bottom wall's two rows are the last two rows of a warp (MODE 4 of half_sweep).
+struct TileDesc {
+  int X0, Y0;    // first column / local row held
+  int y_end;     // rows [Y0, y_end) are held (at most TH of them): rows beyond are treated like rows outside the array
+  int vy0, vy1;  // rows written
+  int pad[3];
+};
+
 struct PackArgs {
   Grid g;
   const float* __restrict__ u_in;
@@ -205,6 +218,7 @@ struct PackArgs {
   ResidentArgs res;
   int tiles_x;           // tiles per tile row (the grid is one-dimensional: blockIdx.x -> order -> tile)
   const int* order;      // tiles sorted by cost, most expensive first (tile_order_kernel), or null for row-major
+  const TileDesc* descs; // or: the pass's tiles as an explicit list, in issue order (one CTA each)
   int extrap_on;  // the step's last pass: apply_extrapolation_at (fluid.cu:720-733) on the tile before it is stored
   int force_on;
   float force_g, force_dt, wt_speed, wt_smoke;
@@ -348,10 +362,12 @@ __device__ __forceinline__ void row_step(u64& U02, u64& U13, u64& vb, u64& vt, c
 }
 
 // One half-sweep over the RY rows of this warp.  Q0 = case of row 0; the case alternates with the row.
-// IRR = false: every row uses the lane's profile multipliers.  IRR = true (a warp with at least one row that
-// differs from the profile): every row fetches its multipliers from the table; s_off holds, per row, the two
-// cases' byte offsets into it (16 bits each).  No per-row branch either way.
-template <int RY, int Q0, bool IRR, bool PRESSURE>
+// MODE 0: every row uses the lane's profile multipliers.  MODE 1 (a warp with rows that differ from the profile, e.g.
+// an obstacle's rim): every row fetches its multipliers from the table; s_off holds, per row, the two cases' byte
+// offsets into it (16 bits each).  MODE 3 / 4: only the warp's first / last two rows differ (the rows at the top /
+// bottom wall): those two take the table path, the others the profile path — decided at compile time per unrolled
+// row, so there is no per-row branch in any mode (a branch per row keeps ptxas from interleaving the rows).
+template <int RY, int Q0, int MODE, bool PRESSURE>
 __device__ __forceinline__ void half_sweep(u64 (&U02)[RY], u64 (&U13)[RY], u64 (&V02)[RY - 1], u64 (&V13)[RY - 1],
                                            const Mult (&prof)[2], u64 o2, int lane, float* sv_top, float* sv_bot,
                                            const unsigned* s_off, const LutEntry* lut, float* sp_warp,
@@ -365,7 +381,7 @@ __device__ __forceinline__ void half_sweep(u64 (&U02)[RY], u64 (&U13)[RY], u64 (
     else vt = c ? V13[r - 1] : V02[r - 1];
     if (r == RY - 1) vb = lds64(sv_bot + 64 * c);
     else vb = c ? V13[r] : V02[r];
-    if (IRR) {
+    if (MODE == 1 || (MODE == 3 && r < 2) || (MODE == 4 && r >= RY - 2)) {
       unsigned word = s_off[r * 32];
       Mult m = lut_load(lut, c ? (word >> 16) : (word & 0xffffu));
       if (c == 0) row_step<0, true, PRESSURE>(U02[r], U13[r], vb, vt, m, o2, lane, pp, pm);
@@ -409,7 +425,14 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   // computed once per tile geometry from the flags) and the open ones fill in behind them.
   const int tile = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
   const int tile_y = tile / a.tiles_x, tile_x = tile - tile_y * a.tiles_x;
-  const int X0 = tile_x * a.stride_x, Y0 = a.row_lo + tile_y * a.stride_y;
+  int X0 = tile_x * a.stride_x, Y0 = a.row_lo + tile_y * a.stride_y;
+  int y_end = a.row_hi;  // held rows end here (a listed tile may end earlier: TileDesc)
+  int dvy0 = 0, dvy1 = 0;
+  if (!RESIDENT && a.descs) {
+    const int4 d = __ldg(reinterpret_cast<const int4*>(a.descs + blockIdx.x));
+    const int d4 = __ldg(&a.descs[blockIdx.x].vy1);
+    X0 = d.x; Y0 = d.y; y_end = d.z; dvy0 = d.w; dvy1 = d4;
+  }
   const int x = X0 + 4 * lane;
   const int lr0 = Y0 + w * RY;
   long long* tl = a.timeline && !RESIDENT ? a.timeline + 5 * (size_t)tile : nullptr;
@@ -432,8 +455,8 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
 
   // rows this tile will write (everything >= halo away from an edge that has a neighbouring tile, clipped to the
   // write window), and — linked slabs in push mode — whether they include edge rows a neighbour is waiting for
-  const int vy0 = max(Y0 == a.row_lo ? a.row_lo : Y0 + a.halo_y, a.write_lo);
-  const int vy1 = min(Y0 + TH >= a.row_hi ? a.row_hi : Y0 + TH - a.halo_y, a.write_hi);
+  const int vy0 = !RESIDENT && a.descs ? dvy0 : max(Y0 == a.row_lo ? a.row_lo : Y0 + a.halo_y, a.write_lo);
+  const int vy1 = !RESIDENT && a.descs ? dvy1 : min(Y0 + TH >= a.row_hi ? a.row_hi : Y0 + TH - a.halo_y, a.write_hi);
   const bool push0 = (a.push.on & 1) && vy0 < a.push.src_hi[0] && vy1 > a.push.src_lo[0];
   const bool push1 = (a.push.on & 2) && vy0 < a.push.src_hi[1] && vy1 > a.push.src_lo[1];
   if (a.push.on && a.push.pass_index > 0) {
@@ -458,7 +481,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
     int lr = lr0 + r;
     float4 uu = make_float4(0.f, 0.f, 0.f, 0.f), vv = uu;
     unsigned f = 0;
-    if (col_ok && lr < a.row_hi) {
+    if (col_ok && lr < y_end) {
       size_t k = (size_t)lr * g.pitch + x;
       // .cg: read through L2 — ghost rows may have been stored by a neighbouring GPU since this SM last saw them,
       // and a tile reads every element exactly once anyway
@@ -486,7 +509,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
 #pragma unroll
     for (int r = 0; r < RY; r++) {
       float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col_ok && lr0 + r < a.row_hi) pv = *reinterpret_cast<const float4*>(a.p + (size_t)(lr0 + r) * g.pitch + x);
+      if (col_ok && lr0 + r < y_end) pv = *reinterpret_cast<const float4*>(a.p + (size_t)(lr0 + r) * g.pitch + x);
       sts64(sp_warp + r * 128, pk(pv.x, pv.z));
       sts64(sp_warp + r * 128 + 64, pk(pv.y, pv.w));
     }
@@ -498,7 +521,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
     const bool whole = x + 3 < g.W;  // the lane that straddles W updates only its real columns
 #pragma unroll
     for (int r = 0; r < RY; r++) {
-      if (!(col_ok && lr0 + r < a.row_hi)) continue;
+      if (!(col_ok && lr0 + r < y_end)) continue;
       u64& p02 = r < RY - 1 ? V02[r < RY - 1 ? r : 0] : vlast02;
       u64& p13 = r < RY - 1 ? V13[r < RY - 1 ? r : 0] : vlast13;
       if (whole) {
@@ -515,7 +538,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
     if (x <= a.inlet_len) {  // inlet: u = speed, smoke = value; tiles overlap and every holder stores the same value
 #pragma unroll
       for (int r = 0; r < RY; r++) {
-        if (!(col_ok && lr0 + r < a.row_hi)) continue;
+        if (!(col_ok && lr0 + r < y_end)) continue;
         float4 uu = make_float4(lo(U02[r]), lo(U13[r]), hi(U02[r]), hi(U13[r]));
         float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
         forces_on_load(a, x, lr0 + r, uu, vv);  // (only its inlet part matters here)
@@ -541,7 +564,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   sts64(sv_bot + 64, vlast13);
   if (w == 0) {
     float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (col_ok && Y0 - 1 >= a.row_lo && Y0 - 1 < a.row_hi) {
+    if (col_ok && Y0 - 1 >= a.row_lo && Y0 - 1 < y_end) {
       vv = __ldcg(reinterpret_cast<const float4*>(a.v_in + (size_t)(Y0 - 1) * g.pitch + x));
       if (FORCES && (!RESIDENT || a.force_on)) {
         float4 unused = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -552,13 +575,14 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
     sts64(sv_top + 64, pk(vv.y, vv.w));
   }
 
-  // Profile = the flags of the lane's middle row; rows that differ anywhere in the warp are irregular.
+  // Profile = the flags of the lane's middle row; a row that differs from it in any lane of the warp is irregular
+  // (bit r of irr_rows, warp-uniform).
   const unsigned pf = fl[RY / 2];
-  bool irr = false;
+  unsigned irr_rows = 0;
   unsigned* s_off = &s_off_all[w][0][lane];
 #pragma unroll
   for (int r = 0; r < RY; r++) {
-    if (fl[r] != pf) irr = true;
+    if (__any_sync(FULL, fl[r] != pf)) irr_rows |= 1u << r;
     s_off[r * 32] = pair_offset(fl[r], 0) | (pair_offset(fl[r], 1) << 16);
   }
   Mult prof[2];
@@ -572,7 +596,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
     prof[c].nT = 0;
   }
   // A profile row must have all its B/T faces open for the unmasked v update to be right; if the middle row is
-  // itself next to a horizontal boundary, fall back to the table for every row that has active cells.
+  // itself next to a horizontal boundary, every row goes through the table.
   {
     bool prof_ok = true;
 #pragma unroll
@@ -580,9 +604,13 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
       unsigned n = (pf >> (8 * k)) & 15u;
       if (n != 0 && (n & (FL_B | FL_T)) != (FL_B | FL_T)) prof_ok = false;
     }
-    if (!prof_ok) irr = true;
+    if (__any_sync(FULL, !prof_ok)) irr_rows = (1u << RY) - 1u;
   }
-  irr = __any_sync(FULL, irr);  // warp-uniform
+  // which half_sweep the warp runs: -1 = none (a listed tile that ends above this warp: it only keeps the barriers)
+  const int sweep_mode = lr0 >= y_end ? -1
+                         : irr_rows == 0 ? 0
+                         : (irr_rows & ~3u) == 0 ? 3
+                         : (irr_rows & ~(3u << (RY - 2))) == 0 ? 4 : 1;
   const u64 o2 = pk(a.o, a.o);
   __syncthreads();
   if (tl && threadIdx.x == 0) tl[1] = globaltimer();
@@ -604,33 +632,66 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
     // flag published, neighbours' flags seen, halo loaded
     long long* rtl = RESIDENT && a.timeline && threadIdx.x == 0 ? a.timeline + ((size_t)tile * nblk + blk) * 6 : nullptr;
     if (rtl) rtl[0] = globaltimer();
-    if (!irr) {
+    if (sweep_mode == 0) {
       for (int it = 0; it < its; it++) {
         if (q == 0) {
-          half_sweep<RY, 0, false, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          half_sweep<RY, 0, 0, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
           __syncthreads();
-          half_sweep<RY, 1, false, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          half_sweep<RY, 1, 0, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
           __syncthreads();
         } else {
-          half_sweep<RY, 1, false, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          half_sweep<RY, 1, 0, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
           __syncthreads();
-          half_sweep<RY, 0, false, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          half_sweep<RY, 0, 0, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+        }
+      }
+    } else if (sweep_mode == 1) {
+      for (int it = 0; it < its; it++) {
+        if (q == 0) {
+          half_sweep<RY, 0, 1, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+          half_sweep<RY, 1, 1, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+        } else {
+          half_sweep<RY, 1, 1, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+          half_sweep<RY, 0, 1, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+        }
+      }
+    } else if (sweep_mode == 3) {
+      for (int it = 0; it < its; it++) {
+        if (q == 0) {
+          half_sweep<RY, 0, 3, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+          half_sweep<RY, 1, 3, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+        } else {
+          half_sweep<RY, 1, 3, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+          half_sweep<RY, 0, 3, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+        }
+      }
+    } else if (sweep_mode == 4) {
+      for (int it = 0; it < its; it++) {
+        if (q == 0) {
+          half_sweep<RY, 0, 4, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+          half_sweep<RY, 1, 4, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+        } else {
+          half_sweep<RY, 1, 4, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          __syncthreads();
+          half_sweep<RY, 0, 4, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
           __syncthreads();
         }
       }
     } else {
       for (int it = 0; it < its; it++) {
-        if (q == 0) {
-          half_sweep<RY, 0, true, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-          __syncthreads();
-          half_sweep<RY, 1, true, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-          __syncthreads();
-        } else {
-          half_sweep<RY, 1, true, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-          __syncthreads();
-          half_sweep<RY, 0, true, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-          __syncthreads();
-        }
+        __syncthreads();
+        __syncthreads();
       }
     }
     if (rtl) rtl[1] = globaltimer();
@@ -764,12 +825,12 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   if (EXTRAP && (!RESIDENT || a.extrap_on)) {
     const int lrA = g.H - 2 - g.row_base, lrB = lrA + 1;  // memory rows of j = 1 and j = 0
     // u(i, H-1) = u(i, H-2): memory rows 0 and 1, both rows of warp 0 of the top tiles
-    if (g.row_base == 0 && Y0 == 0 && w == 0 && a.row_hi >= 2) {
+    if (g.row_base == 0 && Y0 == 0 && w == 0 && y_end >= 2) {
       U02[0] = U02[1];
       U13[0] = U13[1];
     }
     // u(i, 0) = u(i, 1): the two rows may sit in different warps, so row j = 1 travels through shared memory
-    if (lrA >= Y0 && lrA >= 0 && lrB < a.row_hi && lrB < Y0 + TH) {  // uniform over the CTA
+    if (lrA >= Y0 && lrA >= 0 && lrB < y_end && lrB < Y0 + TH) {  // uniform over the CTA
       float4* scratch = reinterpret_cast<float4*>(&sv[0][0]);
 #pragma unroll
       for (int r = 0; r < RY; r++)
@@ -928,6 +989,49 @@ __global__ void tile_order_kernel(const int* __restrict__ cost, int tiles, int* 
   for (int t = threadIdx.x; t < tiles; t += blockDim.x) order[atomicAdd(&start[min(cost[t], 32)], 1)] = t;
 }
 
+// Sweep cost of every listed tile, in tenths of an open warp: a warp costs 10 (profile path), 11 (wall rows from the
+// table), 16 (every row from the table) or nothing (beyond the tile's rows); warp w issues on scheduler w & 3 and a
+// half-sweep ends when the busiest scheduler does, so the tile's cost is the largest of the four sums.  cost[2 t] =
+// that, cost[2 t + 1] = the number of warps on the all-table path.  One CTA per tile, thread layout of the pack kernel.
+__global__ void desc_cost_kernel(Grid g, const uint8_t* __restrict__ flags, int ry, int row_lo, const TileDesc* __restrict__ descs,
+                                 int* __restrict__ cost) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const TileDesc d = descs[blockIdx.x];
+  const int x = d.X0 + 4 * lane, lr0 = d.Y0 + w * ry;
+  auto flag_word = [&](int r) -> unsigned {
+    int lr = lr0 + r;
+    unsigned f = 0;
+    if (x < g.pitch && lr < d.y_end) f = *reinterpret_cast<const unsigned*>(flags + (size_t)lr * g.pitch + x);
+    if (lane == 31) f &= 0x00ffffffu;
+    if (lr == row_lo) f = 0;
+    return f;
+  };
+  const unsigned pf = flag_word(ry / 2);
+  unsigned irr_rows = 0;
+  for (int r = 0; r < ry; r++)
+    if (__any_sync(FULL, flag_word(r) != pf)) irr_rows |= 1u << r;
+  bool prof_ok = true;
+  for (int k = 0; k < 4; k++) {
+    unsigned n = (pf >> (8 * k)) & 15u;
+    if (n != 0 && (n & (FL_B | FL_T)) != (FL_B | FL_T)) prof_ok = false;
+  }
+  if (__any_sync(FULL, !prof_ok)) irr_rows = (1u << ry) - 1u;
+  const int units = lr0 >= d.y_end ? 0 : irr_rows == 0 ? 10 : ((irr_rows & ~3u) == 0 || (irr_rows & ~(3u << (ry - 2))) == 0) ? 11 : 16;
+  __shared__ int s_sched[4], s_table;
+  if (threadIdx.x < 4) s_sched[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_table = 0;
+  __syncthreads();
+  if (lane == 0) {
+    atomicAdd(&s_sched[w & 3], units);
+    if (units == 16) atomicAdd(&s_table, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cost[2 * blockIdx.x] = max(max(s_sched[0], s_sched[1]), max(s_sched[2], s_sched[3]));
+    cost[2 * blockIdx.x + 1] = s_table;
+  }
+}
+
 struct Variant {
   int ry, nw;
   void (*kernel[6])(PackArgs);  // indexed by (forces on load) | (extrapolation before store) << 1; [4] = with pressure;
@@ -1025,8 +1129,103 @@ const int* tile_order(Sim* s, int variant, int it, const Geometry& q, int row_lo
     cudaFree(buf);
     return nullptr;
   }
-  s->orders[s->n_orders++] = {variant, it, row_lo, row_hi, edge_first, buf};
+  s->orders[s->n_orders++] = {variant, it, row_lo, row_hi, edge_first, buf, 0};
   return buf;
+}
+
+// The explicit tile list of a whole-domain pass (TileDesc): the regular grid with (1) its last tile row moved up so
+// that the array's last two rows end a warp, (2) every tile whose busiest scheduler carries much more than four open
+// warps' worth of work (an obstacle rim: warps on the all-table path) cut in two along y, (3) the tiles sorted by
+// cost, most expensive first.  Built once per geometry outside graph capture (costs are read back) and cached with
+// the issue orders; null when the option is off, the cache is full or a graph is being captured.
+const TileDesc* tile_descs(Sim* s, int variant, int it, const Geometry& q, int* n_out) {
+  *n_out = 0;
+  if (!s->split_tiles) return nullptr;
+  const int rows = s->g.local_rows;
+  for (int k = 0; k < s->n_orders; k++)
+    if (s->orders[k].variant == variant && s->orders[k].it == it && s->orders[k].row_lo == 0 && s->orders[k].row_hi == rows &&
+        s->orders[k].edge_first == -1) {
+      *n_out = s->orders[k].n_descs;
+      return reinterpret_cast<const TileDesc*>(s->orders[k].order);
+    }
+  if (s->n_orders == Sim::kMaxOrders) return nullptr;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s->stream, &cap);
+  if (cap != cudaStreamCaptureStatusNone) return nullptr;
+  const Variant& v = kVariants[variant];
+  const int th = v.ry * v.nw;
+  std::vector<TileDesc> tiles;
+  for (int ty = 0; ty < q.tiles_y; ty++)
+    for (int tx = 0; tx < q.tiles_x; tx++) {
+      TileDesc d = {};
+      d.X0 = tx * q.stride_x;
+      d.Y0 = ty * q.stride_y;
+      d.vy0 = ty == 0 ? 0 : d.Y0 + q.halo_y;
+      d.vy1 = d.Y0 + th >= rows ? rows : d.Y0 + th - q.halo_y;
+      d.y_end = d.Y0 + th < rows ? d.Y0 + th : rows;
+      if (ty == q.tiles_y - 1 && ty > 0) d.Y0 -= (v.ry - (rows - d.Y0) % v.ry) % v.ry;  // the last rows end a warp
+      tiles.push_back(d);
+    }
+  int* d_buf = nullptr;   // descriptors, then two ints of cost per tile (sized for every tile being split)
+  const size_t cap_tiles = 2 * tiles.size();
+  if (cudaMalloc(&d_buf, cap_tiles * (sizeof(TileDesc) + 2 * sizeof(int))) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  TileDesc* d_descs = reinterpret_cast<TileDesc*>(d_buf);
+  int* d_cost = reinterpret_cast<int*>(d_descs + cap_tiles);
+  std::vector<int> cost;
+  auto evaluate = [&]() -> bool {
+    cost.assign(2 * tiles.size(), 0);
+    if (cudaMemcpyAsync(d_descs, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s->stream) != cudaSuccess) return false;
+    desc_cost_kernel<<<(int)tiles.size(), v.nw * 32, 0, s->stream>>>(s->g, s->flags, v.ry, 0, d_descs, d_cost);
+    if (cudaMemcpyAsync(cost.data(), d_cost, cost.size() * sizeof(int), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) return false;
+    return cudaStreamSynchronize(s->stream) == cudaSuccess;
+  };
+  bool ok = evaluate();
+  if (ok) {  // cut the expensive tiles in two (at most an eighth of the tiles)
+    std::vector<TileDesc> out;
+    int cuts = 0;
+    const int max_cuts = (int)tiles.size() / 8 + 1;
+    for (size_t t = 0; t < tiles.size(); t++) {
+      const TileDesc& d = tiles[t];
+      const int owned = d.vy1 - d.vy0;
+      if (cost[2 * t] > 46 && cost[2 * t + 1] >= 3 && owned >= 4 * v.ry && cuts < max_cuts) {
+        const int mid = d.vy0 + owned / 2;
+        TileDesc a = d, b = d;
+        a.vy1 = mid;
+        a.y_end = mid + q.halo_y < d.y_end ? mid + q.halo_y : d.y_end;
+        b.vy0 = mid;
+        b.Y0 = mid - q.halo_y > d.Y0 ? mid - q.halo_y : d.Y0;
+        out.push_back(a);
+        out.push_back(b);
+        cuts++;
+      } else {
+        out.push_back(d);
+      }
+    }
+    if (cuts) {
+      tiles.swap(out);
+      ok = evaluate();
+    }
+  }
+  if (ok) {  // most expensive first
+    std::vector<int> idx(tiles.size());
+    for (size_t t = 0; t < idx.size(); t++) idx[t] = (int)t;
+    std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return cost[2 * x] > cost[2 * y]; });
+    std::vector<TileDesc> sorted(tiles.size());
+    for (size_t t = 0; t < idx.size(); t++) sorted[t] = tiles[idx[t]];
+    ok = cudaMemcpyAsync(d_descs, sorted.data(), sorted.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s->stream) == cudaSuccess &&
+         cudaStreamSynchronize(s->stream) == cudaSuccess;
+  }
+  if (!ok) {
+    cudaGetLastError();
+    cudaFree(d_buf);
+    return nullptr;
+  }
+  s->orders[s->n_orders++] = {variant, it, 0, rows, -1, d_buf, (int)tiles.size()};
+  *n_out = (int)tiles.size();
+  return d_descs;
 }
 
 // The passes of one projection call: ceil(iterations / T) passes of nearly equal size (25 at T = 10 -> 9, 8, 8 rather
@@ -1278,8 +1477,12 @@ int run_passes(Sim* s, int variant, int T, int iterations, float d_t, bool with_
     if (s->d_timeline && (size_t)q.tiles_x * q.tiles_y * 5 > s->timeline_cap) a.timeline = nullptr;
     s->timeline_tiles = a.timeline ? q.tiles_x * q.tiles_y : 0;
     a.tiles_x = q.tiles_x;
-    a.order = tile_order(s, variant, it, q, pl.row_lo, pl.row_hi, push_sides);
-    int r = launch_pass(s, v, a, dim3(q.tiles_x * q.tiles_y), s->stream);
+    int n_descs = 0;
+    if (!push_sides && ghost_depth < 0 && pl.row_lo == 0 && pl.row_hi == s->g.local_rows)
+      a.descs = tile_descs(s, variant, it, q, &n_descs);
+    if (a.descs && a.timeline) s->timeline_tiles = n_descs;
+    if (!a.descs) a.order = tile_order(s, variant, it, q, pl.row_lo, pl.row_hi, push_sides);
+    int r = launch_pass(s, v, a, dim3(a.descs ? n_descs : q.tiles_x * q.tiles_y), s->stream);
     if (r != SAYAL_OK) return r;
     float* t = s->u; s->u = s->u_buf; s->u_buf = t;  // ping-pong: neighbouring tiles still read the old halo
     t = s->v; s->v = s->v_buf; s->v_buf = t;
@@ -1465,7 +1668,10 @@ int tiled_prepare(Sim* s, int iterations) {
     const int passes = (iterations + s->plan_T - 1) / s->plan_T;
     for (int it = iterations / passes; !s->plan_resident && it <= (iterations + passes - 1) / passes; it++) {
       Geometry q;
-      if (it > 0 && geometry(s->g, kVariants[s->plan_variant], it, &q)) tile_order(s, s->plan_variant, it, q, 0, s->g.local_rows);
+      if (it > 0 && geometry(s->g, kVariants[s->plan_variant], it, &q)) {
+        int n_descs = 0;
+        if (!tile_descs(s, s->plan_variant, it, q, &n_descs)) tile_order(s, s->plan_variant, it, q, 0, s->g.local_rows);
+      }
     }
   }
   if (s->n_plans == Sim::kMaxPlans) s->n_plans = 0;  // full: start over (never happens with <= 8 chunk sizes)

@@ -189,6 +189,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   s->shrink_window = 1;
   s->proj_depth = -1;
   s->order_tiles = 1;
+  s->split_tiles = 1;
   s->advect_kernel = 2;
   s->overlap_exchange = 1;
   s->slab_push = 1;
@@ -211,6 +212,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   if (const char* e = getenv("SAYAL_USE_PDL")) s->use_pdl = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_FUSE_FORCES")) s->fuse_forces = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_ORDER_TILES")) s->order_tiles = atoi(e) != 0;
+  if (const char* e = getenv("SAYAL_SPLIT_TILES")) s->split_tiles = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_SHRINK_WINDOW")) s->shrink_window = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_FUSE_EXTRAPOLATION")) s->fuse_extrapolation = atoi(e) != 0;
   if (const char* e = getenv("SAYAL_SLAB_PUSH")) s->slab_push = atoi(e) != 0;
@@ -1037,6 +1039,9 @@ int sayal_set_option(sayal_sim* sim, const char* key, int64_t value) {
     s->fuse_extrapolation = value != 0;
   } else if (!strcmp(key, "shrink_window")) {
     s->shrink_window = value != 0;
+  } else if (!strcmp(key, "split_tiles")) {
+    s->split_tiles = value != 0;
+    s->plan_variant = -1, s->n_plans = 0;
   } else if (!strcmp(key, "debug_events")) {
     s->debug_events = value != 0;
   } else if (!strcmp(key, "resident")) {
@@ -1078,6 +1083,7 @@ int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value) {
   else if (!strcmp(key, "shrink_window")) *value = s->shrink_window;
   else if (!strcmp(key, "slab_push")) *value = s->slab_push;
   else if (!strcmp(key, "resident")) *value = s->resident;
+  else if (!strcmp(key, "split_tiles")) *value = s->split_tiles;
   else if (!strcmp(key, "plan_resident")) *value = s->plan_resident;
   else if (!strcmp(key, "push_mode")) *value = push_mode(s) ? 1 : 0;
   else if (!strcmp(key, "fuse_extrapolation")) *value = s->fuse_extrapolation;

@@ -195,8 +195,9 @@ struct Sim {
   char plan_log[2048];     // candidates of the last tuning (sayal_plan_log)
   // issue order of the tiles (most expensive first) per tile geometry, built on first use (projection_pack.cu)
   int order_tiles;        // option (default 1)
-  static constexpr int kMaxOrders = 64;
-  struct TileOrder { int variant, it, row_lo, row_hi, edge_first; int* order; } orders[kMaxOrders];
+  static constexpr int kMaxOrders = 256;
+  struct TileOrder { int variant, it, row_lo, row_hi, edge_first; int* order; int n_descs; } orders[kMaxOrders];  // edge_first -1: `order` holds a tile list (TileDesc)
+  int split_tiles;        // option (default 1): whole-domain passes run over an explicit tile list (projection_pack.cu)
   int n_orders;
   // CUDA graph cache for sayal_run: one single-step graph per starting buffer parity, with the
   // pointer assignment the step leaves behind (the step swaps front and back buffers)

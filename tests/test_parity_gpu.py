@@ -164,6 +164,30 @@ def test_resident_full_size_equals_tiled_passes():
         assert np.array_equal(out[0][n].view(np.uint32), out[1][n].view(np.uint32)), n
 
 
+@pytest.mark.parametrize("height,cy,radius", [(470, 235, 60.0), (333, 100, 45.0), (391, 300, 80.0)])
+@pytest.mark.parametrize("rows,T", [(8, 4), (12, 8), (10, 5)])
+def test_listed_tiles_cut_and_shifted_change_no_bit(height, cy, radius, rows, T):
+    """Whole-domain passes run over an explicit tile list: obstacle tiles cut in two along y, the last tile row moved up
+    so that the bottom wall ends a warp, wall rows from the table at compile-time positions.  Same bits as the oracle
+    (and hence as the regular grid), with a large disc that makes several tiles expensive."""
+    cfg = baseline_config(1, width=520, height=height)
+    cfg["sim.obstacle.center_x"] = 260
+    cfg["sim.obstacle.center_y"] = cy
+    cfg["sim.obstacle.radius"] = radius
+    gpu, cpu = pair(cfg)
+    gpu.set_option("resident", 0)
+    gpu.set_option("temporal_block", T)
+    gpu.set_option("tile_rows_per_warp", rows)
+    assert gpu.get_option("split_tiles") == 1
+    gpu.stage_projection(2 * T + 1, 0.05)
+    cpu.projection(2 * T + 1, 0.05)
+    assert_same(gpu, cpu, names=("u", "v"), what=f"listed tiles {height} {rows} {T}")
+    gpu.run(2)  # and through whole steps (forces on load, extrapolation before store)
+    cpu.step(None, cfg.c.d_t)
+    cpu.step(None, cfg.c.d_t)
+    assert_same(gpu, cpu, what="listed tiles, steps")
+
+
 def test_projection_with_pressure_and_range():
     cfg = baseline_config(0)
     gpu, cpu = pair(cfg)
