@@ -408,7 +408,9 @@ __device__ __forceinline__ void half_sweep(u64 (&U02)[RY], u64 (&U13)[RY], u64 (
 // leaves them, and nothing else depends on p.
 // RESIDENT: the whole projection in one launch, tiles kept in registers between sweep blocks (ResidentArgs); forces and
 // extrapolation are compiled in and switched by a.force_on / a.extrap_on.
-template <int RY, int NW, bool FORCES, bool EXTRAP, bool PRESSURE, bool RESIDENT = false>
+// PUSH: the pass of a linked slab that stores its edge rows into the neighbours (PushArgs); compiled out of every other
+// instantiation (the store phase runs once per tile, cold: every instruction less is an instruction-cache line less).
+template <int RY, int NW, bool FORCES, bool EXTRAP, bool PRESSURE, bool RESIDENT = false, bool PUSH = false>
 __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a) {
   extern __shared__ __align__(16) float sp[];  // PRESSURE only
   constexpr int TH = RY * NW;
@@ -457,9 +459,9 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   // write window), and — linked slabs in push mode — whether they include edge rows a neighbour is waiting for
   const int vy0 = !RESIDENT && a.descs ? dvy0 : max(Y0 == a.row_lo ? a.row_lo : Y0 + a.halo_y, a.write_lo);
   const int vy1 = !RESIDENT && a.descs ? dvy1 : min(Y0 + TH >= a.row_hi ? a.row_hi : Y0 + TH - a.halo_y, a.write_hi);
-  const bool push0 = (a.push.on & 1) && vy0 < a.push.src_hi[0] && vy1 > a.push.src_lo[0];
-  const bool push1 = (a.push.on & 2) && vy0 < a.push.src_hi[1] && vy1 > a.push.src_lo[1];
-  if (a.push.on && a.push.pass_index > 0) {
+  const bool push0 = PUSH && (a.push.on & 1) && vy0 < a.push.src_hi[0] && vy1 > a.push.src_lo[0];
+  const bool push1 = PUSH && (a.push.on & 2) && vy0 < a.push.src_hi[1] && vy1 > a.push.src_lo[1];
+  if (PUSH && a.push.on && a.push.pass_index > 0) {
     // The neighbour's previous pass stored its edge rows into my ghost rows: the warps that load such rows (and
     // warp 0 of a tile that pushes, which must not overwrite rows the neighbour may still be reading) wait for its
     // flag; every other warp goes straight to its loads and the wait hides behind them.
@@ -893,7 +895,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
           u64 q02 = lds64(sp_warp + r * 128), q13 = lds64(sp_warp + r * 128 + 64);
           *reinterpret_cast<float4*>(a.p + k) = make_float4(lo(q02), lo(q13), hi(q02), hi(q13));
         }
-        if (a.push.debug & 1) continue;
+        if (!PUSH || (a.push.debug & 1)) continue;
         if (push0 && lr >= a.push.src_lo[0] && lr < a.push.src_hi[0]) {  // my edge rows = the neighbour's ghost rows
           size_t kp = (size_t)(lr - a.push.src_lo[0] + a.push.dst_row0[0]) * g.pitch + x;
           *reinterpret_cast<float4*>(a.push.peer_u[0] + kp) = uo;
@@ -907,7 +909,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
       }
     }
   }
-  if (push0 || push1) {  // uniform over the CTA
+  if (PUSH && (push0 || push1)) {  // uniform over the CTA
     __syncthreads();     // every thread's stores are issued before thread 0 fences at system scope
     if (threadIdx.x == 0) {
       if (!(a.push.debug & 2)) __threadfence_system();
@@ -1036,11 +1038,16 @@ struct Variant {
   int ry, nw;
   void (*kernel[6])(PackArgs);  // indexed by (forces on load) | (extrapolation before store) << 1; [4] = with pressure;
                                 // [5] = resident (whole projection in one launch, forces / extrapolation by flag)
+  void (*push_kernel[4])(PackArgs);  // the first four again, for passes that push their edge rows (linked slabs)
 };
 #define SAYAL_PACK_VARIANT(RY, NW)                                                                                        \
   {RY, NW, {projection_pack_kernel<RY, NW, false, false, false>, projection_pack_kernel<RY, NW, true, false, false>,     \
             projection_pack_kernel<RY, NW, false, true, false>, projection_pack_kernel<RY, NW, true, true, false>,       \
-            projection_pack_kernel<RY, NW, false, false, true>, projection_pack_kernel<RY, NW, true, true, false, true>}}
+            projection_pack_kernel<RY, NW, false, false, true>, projection_pack_kernel<RY, NW, true, true, false, true>},  \
+           {projection_pack_kernel<RY, NW, false, false, false, false, true>,                                            \
+            projection_pack_kernel<RY, NW, true, false, false, false, true>,                                             \
+            projection_pack_kernel<RY, NW, false, true, false, false, true>,                                             \
+            projection_pack_kernel<RY, NW, true, true, false, false, true>}}
 const Variant kVariants[] = {SAYAL_PACK_VARIANT(8, 16), SAYAL_PACK_VARIANT(10, 16), SAYAL_PACK_VARIANT(12, 16)};
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kMaxT = 16;
@@ -1091,7 +1098,9 @@ int launch_pass(Sim* s, const Variant& v, const PackArgs& a, dim3 grid, cudaStre
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr;
   lc.numAttrs = s->use_pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&lc, a.p ? v.kernel[4] : v.kernel[(a.force_on ? 1 : 0) | (a.extrap_on ? 2 : 0)], a);
+  const int which = (a.force_on ? 1 : 0) | (a.extrap_on ? 2 : 0);
+  if (a.push.on && a.p) return set_error(SAYAL_EINVAL, "projection push: not available with enable_pressure");
+  cudaError_t e = cudaLaunchKernelEx(&lc, a.p ? v.kernel[4] : a.push.on ? v.push_kernel[which] : v.kernel[which], a);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
     char m[256];
@@ -1502,7 +1511,8 @@ int tiled_max_temporal_block() { return kMaxT; }
 int tiled_preload() {
   {
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, tile_cost_kernel) != cudaSuccess || cudaFuncGetAttributes(&fa, tile_order_kernel) != cudaSuccess)
+    if (cudaFuncGetAttributes(&fa, tile_cost_kernel) != cudaSuccess || cudaFuncGetAttributes(&fa, tile_order_kernel) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa, desc_cost_kernel) != cudaSuccess)
       return set_error(SAYAL_ECUDA, "preload: tile order kernels");
   }
   for (int v = 0; v < kNumVariants; v++)
@@ -1513,6 +1523,7 @@ int tiled_preload() {
         e = cudaFuncSetAttribute(kVariants[v].kernel[4], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pressure_smem(kVariants[v]));
       if (e == cudaSuccess && m == 5)
         e = cudaFuncSetAttribute(kVariants[v].kernel[5], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResidentStageMax);
+      if (e == cudaSuccess && m < 4) e = cudaFuncGetAttributes(&fa, kVariants[v].push_kernel[m]);
       if (e != cudaSuccess) return set_error(SAYAL_ECUDA, cudaGetErrorString(e));
     }
   return SAYAL_OK;
@@ -1651,6 +1662,9 @@ int tiled_prepare(Sim* s, int iterations) {
     if (spres) cudaFree(spres);
     cudaGetLastError();
   }
+  if (!timed)  // a resident plan is only ever chosen on a measurement (its model is rough): untimed, take the best other
+    for (int c = 0; c < nc; c++)
+      if (!cands[c].resident) { best = c; break; }
   s->plan_variant = cands[best].variant;
   s->plan_T = cands[best].T;
   s->plan_resident = cands[best].resident;

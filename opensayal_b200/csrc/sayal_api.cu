@@ -509,6 +509,7 @@ bool is_linked(const Sim* s) { return s->link_block && (s->link.peer_recv[0] || 
 // neighbours' velocity arrays (every link made through this library has them) and at least two ghost rows.
 bool push_mode(const Sim* s) {
   if (!is_linked(s) || !s->slab_push || s->projection_kernel != 1 || s->cfg.proj_n <= 0 || s->slab_halo < 2) return false;
+  if (s->ph.enable_pressure) return false;  // the pressure instantiation has no push code: exchange kernels between chunks
   for (int d = 0; d < 2; d++)
     if (s->link.peer_words[d] && !s->peer_vel[d][0]) return false;
   return true;

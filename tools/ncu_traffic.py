@@ -21,7 +21,7 @@ for r in data:
         b += float(r[col[k]].replace(",", "")) * scale[units[col[k]]]
     vals.append(b)
     times.append(float(r[col["gpu__time_duration.sum"]].replace(",", "")))
-plan = json.load(open(plan_json))["config"]
+plan = json.load(open(plan_json))["plan"]
 res = {"kernel": sorted(names)[0] if names else None, "temporal_block": plan["temporal_block"],
        "rows_per_warp": plan["tile_rows_per_warp"], "dram_bytes_per_launch": sum(vals) / len(vals), "launches": len(vals),
        "ncu_time_us_per_launch": sum(times) / len(times), "source": rep.split("/")[-1] + " (dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches)"}
