@@ -824,7 +824,12 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   // j-rules, then all i-rules; see extrapolation_kernel in kernels_basic.cu) applied to the registers.  Every
   // source value sits in the same tile as its destination: rows j = 0, 1 (and H-1, H-2) are the last (first) two
   // rows of the domain, inside the un-haloed edge of the tiles that hold them; columns 0, 1 share a lane.
-  if (EXTRAP && (!RESIDENT || a.extrap_on)) {
+  // Only tiles that hold a border row or column have anything to extrapolate (uniform over the CTA): rows j = H-1,
+  // H-2 (memory rows 0, 1 of the domain), j = 1, 0, columns 0, 1 and W-1.
+  const bool extrap_tile = EXTRAP && (!RESIDENT || a.extrap_on) &&
+                           (X0 == 0 || (((g.W - 1) & ~3) >= X0 && ((g.W - 1) & ~3) < X0 + TW) || g.row_base + Y0 <= 1 ||
+                            (g.H - 2 - g.row_base < Y0 + TH && g.H - 1 - g.row_base >= Y0));
+  if (extrap_tile) {
     const int lrA = g.H - 2 - g.row_base, lrB = lrA + 1;  // memory rows of j = 1 and j = 0
     // u(i, H-1) = u(i, H-2): memory rows 0 and 1, both rows of warp 0 of the top tiles
     if (g.row_base == 0 && Y0 == 0 && w == 0 && y_end >= 2) {
