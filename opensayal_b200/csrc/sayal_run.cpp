@@ -2,10 +2,13 @@
 // /root/reference/src/main.cu:42-107 (ConfigParser().parse(); Fluid fluid(config); loop { fluid.update }).
 //
 //   sayal_run [--config OpenSayal.conf.json] [--steps N] [--device D] [--dump PREFIX] [--frames PREFIX]
-//             [--every K] [--plain] [--temporal-block T] [--no-graph]
+//             [--every K] [--plain] [--temporal-block T] [--no-graph] [--real-time]
 //
 // Like the reference it reads ./OpenSayal.conf.json by default (config_parser.cpp:13) and steps with
-// sim.time.d_t (main.cu:91-95; real-time d_t needs a display loop and is not offered headless).
+// sim.time.d_t, or — with sim.time.enable_real_time in the config or --real-time on the command line — with the
+// wall-clock time that passed since the previous loop iteration times sim.time.real_time_multiplier, the first step
+// with d_t = 0, exactly as main.cu:72-95 does (one sayal_step + sayal_sync per iteration: d_t changes every step, so
+// there is no graph to replay; the reference also blocks once per step, fluid.cu:794).
 // --dump writes raw little-endian fp32 fields (reference layout) every K steps.
 // --frames writes what graphics.update(fluid, d_t) (main.cu:98) would have shown every K steps, as binary PPM:
 // the RGBA frame of graphics_handler.cu:258-302 with, when visual.path_line.enable / visual.arrows.enable are set,
@@ -102,7 +105,7 @@ static bool write_frame(sayal_sim* sim, const sayal_config& c, const sayal_visua
 int main(int argc, char** argv) {
   std::string config_path = "OpenSayal.conf.json", dump_prefix, frames_prefix;
   int steps = 100, device = 0, every = 0, temporal_block = -1;
-  bool plain = false, no_graph = false;
+  bool plain = false, no_graph = false, real_time = false;
   for (int k = 1; k < argc; k++) {
     auto need = [&](const char* flag) -> const char* {
       if (k + 1 >= argc) {
@@ -120,10 +123,11 @@ int main(int argc, char** argv) {
     else if (!std::strcmp(argv[k], "--temporal-block")) temporal_block = std::atoi(need("--temporal-block"));
     else if (!std::strcmp(argv[k], "--plain")) plain = true;
     else if (!std::strcmp(argv[k], "--no-graph")) no_graph = true;
+    else if (!std::strcmp(argv[k], "--real-time")) real_time = true;
     else {
       std::fprintf(stderr,
                    "usage: sayal_run [--config FILE] [--steps N] [--device D] [--dump PREFIX] [--frames PREFIX] [--every K] "
-                   "[--plain] [--temporal-block T] [--no-graph]\n");
+                   "[--plain] [--temporal-block T] [--no-graph] [--real-time]\n");
       return 1;  // main.cu:19-25 exits 1 on bad argv
     }
   }
@@ -153,10 +157,30 @@ int main(int argc, char** argv) {
     frames_in_flight--;
     return write_frame(sim, cfg, vis, px, frames_prefix, (long long)at) ? SAYAL_OK : SAYAL_EIO;
   };
+  real_time = real_time || cfg.enable_real_time != 0;
+  bool have_prev = false;
+  std::chrono::steady_clock::time_point prev_time;
+  double simulated = 0.0;
   while (done < steps) {
     int chunk = (every > 0 && outputs) ? std::min(every, steps - done) : steps - done;
-    r = sayal_run(sim, chunk, cfg.d_t);
-    if (r != SAYAL_OK) return die("sayal_run", r);
+    if (real_time) {  // main.cu:72-95: d_t = time since the previous iteration x multiplier (0 on the first one)
+      const sayal_source idle = {0, 0.f, 0.f, 0, 0};
+      for (int k = 0; k < chunk; k++) {
+        const auto now = std::chrono::steady_clock::now();
+        if (!have_prev) prev_time = now, have_prev = true;
+        const long long ns = std::chrono::duration_cast<std::chrono::nanoseconds>(now - prev_time).count();
+        const float d_t = (ns != 0 ? (float)ns / 1000000000 : 0.f) * cfg.real_time_multiplier;
+        r = sayal_step(sim, &idle, d_t);
+        if (r == SAYAL_OK) r = sayal_sync(sim);
+        if (r != SAYAL_OK) return die("sayal_step", r);
+        simulated += d_t;
+        prev_time = now;
+      }
+    } else {
+      r = sayal_run(sim, chunk, cfg.d_t);
+      if (r != SAYAL_OK) return die("sayal_run", r);
+      simulated += (double)chunk * cfg.d_t;
+    }
     done += chunk;
     if (!dump_prefix.empty() && !dump(sim, cfg, dump_prefix, done)) return die("dump", -1);
     if (!frames_prefix.empty()) {
@@ -175,9 +199,9 @@ int main(int argc, char** argv) {
   double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   float mn = 0, mx = 0;
   if (cfg.enable_pressure) sayal_pressure_range(sim, &mn, &mx);
-  std::printf("{\"width\": %d, \"height\": %d, \"steps\": %d, \"seconds\": %.6f, \"cell_steps_per_s\": %.4e, "
+  std::printf("{\"width\": %d, \"height\": %d, \"steps\": %d, \"seconds\": %.6f, \"simulated_seconds\": %.6f, \"cell_steps_per_s\": %.4e, "
               "\"kernel_launches\": %lld, \"min_pressure\": %g, \"max_pressure\": %g}\n",
-              cfg.width, cfg.height, steps, sec, (double)cfg.width * cfg.height * steps / sec,
+              cfg.width, cfg.height, steps, sec, simulated, (double)cfg.width * cfg.height * steps / sec,
               (long long)sayal_launch_count(sim), mn, mx);
   sayal_destroy(sim);
   return 0;

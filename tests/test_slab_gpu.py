@@ -174,6 +174,53 @@ def test_native_slabs_report_a_too_small_margin():
     assert errors == 0 and overflow > 0
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_linked_slabs_share_one_pressure_range_and_frame(world):
+    """Fluid::min_pressure / max_pressure are ONE pair for the frame (fluid.cu:778-787, graphics_handler.cu:288-289):
+    linked slabs reduce their ranges along the chain inside the step, so every slab reports the single-domain pair and
+    the slabs' pressure frames, stacked, are the single-domain frame bit for bit."""
+    from opensayal_b200 import Fluid as F
+    cfg = baseline_config(0, width=256, height=288)  # gravity tank, enable_pressure
+    cfg["sim.projection.n"] = 12
+    c = cfg.c
+    u, v, sm = synthetic_fields(c.width, c.height)
+    single = F(cfg, device=0)
+    for n, a in (("u", u), ("v", v), ("smoke", sm)):
+        single.set_field(n, a)
+    single.run(3)
+    single.sync()
+    want_range = (single.min_pressure, single.max_pressure)
+    want_frame = single.render_pixels()
+    want_p = single.get_field("p")
+    single.close()
+    sims = []
+    for r in range(world):
+        row0, rows = S.slab_rows(c.height, world, r)
+        f = F(cfg, device=0, slab=(row0, rows, 20))
+        f.set_option("advect_margin", 6)
+        for n, a in (("u", u), ("v", v), ("smoke", sm)):
+            f.set_field(n, a[row0:row0 + rows])
+        sims.append(f)
+    S.link_local(sims)
+    for f in sims:
+        f.run(0)
+    for f in sims:
+        f.slab_exchange(S.F_U | S.F_V | S.F_SMOKE)
+    for _ in range(3):
+        for f in sims:
+            f.run(1)
+    for f in sims:
+        f.sync()
+    assert np.array_equal(np.concatenate([f.get_field("p") for f in sims]), want_p)
+    for f in sims:
+        assert (f.min_pressure, f.max_pressure) == want_range
+    assert want_range[0] < 0.0 < want_range[1]
+    frame = np.concatenate([f.render_pixels() for f in sims])
+    assert np.array_equal(frame, want_frame)
+    for f in sims:
+        f.close()
+
+
 def test_silent_neighbour_raises_a_sticky_link_error():
     """A linked slab whose neighbour never steps: the waits give up after 2 s, nothing is unpacked, and every later
     synchronising call reports SAYAL_ELINK instead of handing out fields (no silent corruption)."""

@@ -413,3 +413,27 @@ def test_sayal_run_writes_frames_asynchronously(tmp_path):
     assert raw.startswith(header)
     rgb = np.frombuffer(raw[len(header):], np.uint8).reshape(54, 96, 3)
     assert np.array_equal(rgb, channels(px)[..., :3].astype(np.uint8))
+
+
+@pytest.mark.gpu
+def test_sayal_run_real_time_steps(tmp_path):
+    """--real-time / sim.time.enable_real_time: d_t = wall-clock time since the previous iteration x the multiplier,
+    0 on the first iteration (main.cu:72-95); the run reports the simulated time, which must be positive, below the
+    wall time x multiplier, and the fields must stay finite."""
+    import json
+    import subprocess
+    from opensayal_b200 import LIB_PATH
+    conf = {"sim": {"width": 96, "height": 54, "enable_pressure": False, "enable_smoke": True,
+                    "time": {"enable_real_time": True, "real_time_multiplier": 0.5},
+                    "wind_tunnel": {"speed": 40.0, "pipe_height": 14, "smoke_height": 6}, "projection": {"n": 10}},
+            "fluid": {"viscosity": 0.0}}
+    path = tmp_path / "OpenSayal.conf.json"
+    path.write_text(json.dumps(conf))
+    exe = LIB_PATH.parent / "sayal_run"
+    out = subprocess.run([str(exe), "--config", str(path), "--steps", "20", "--dump", str(tmp_path / "d")],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert 0.0 < line["simulated_seconds"] <= 0.5 * line["seconds"]
+    u = np.fromfile(tmp_path / "d_u_000020.f32", dtype=np.float32)
+    assert u.size == 96 * 54 and np.isfinite(u).all()
