@@ -150,6 +150,20 @@ def test_native_linked_slabs_bit_identical_to_single_gpu(world, halo, graph):
         assert np.array_equal(got[n], want[n]), n
 
 
+def test_native_linked_slabs_with_default_viscosity():
+    """fluid.viscosity = 0.001 (the reference's shipped default, config_parser.cpp:117): the linked step carries the
+    diffusion sweeps chunked by the halo with an exchange of u after each chunk; same bits as one GPU."""
+    cfg = baseline_config(1, width=384, height=420)
+    cfg["sim.projection.n"] = 20
+    cfg["sim.wind_tunnel.speed"] = 60.0
+    cfg["fluid.viscosity"] = 0.001
+    want, _ = run_single(cfg, 2)
+    got, overflow, errors = run_slabs_native(cfg, 3, 16, 2, graph=1)
+    assert errors == 0 and overflow == 0
+    for n in ("u", "v", "smoke"):
+        assert np.array_equal(got[n], want[n]), n
+
+
 @pytest.mark.parametrize("overlap", [0, 1])
 def test_native_slabs_tall_domain_split_last_pass(overlap, monkeypatch):
     """Tall slabs (several tile rows each): with overlap on, the last projection pass of a chunk runs as edge tile
