@@ -44,6 +44,7 @@ namespace {
 typedef unsigned long long u64;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int TW = 128;  // tile width: 32 lanes x 4 cells
+constexpr bool kWallModes = false;  // half_sweep modes 3 / 4 (see the kernel)
 
 // ---- packed fp32 pairs (element 0 = low register) ------------------------------------------------------
 __device__ __forceinline__ u64 pk(float lo, float hi) {
@@ -608,11 +609,14 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
     }
     if (__any_sync(FULL, !prof_ok)) irr_rows = (1u << RY) - 1u;
   }
-  // which half_sweep the warp runs: -1 = none (a listed tile that ends above this warp: it only keeps the barriers)
-  const int sweep_mode = lr0 >= y_end ? -1
-                         : irr_rows == 0 ? 0
-                         : (irr_rows & ~3u) == 0 ? 3
-                         : (irr_rows & ~(3u << (RY - 2))) == 0 ? 4 : 1;
+  // which half_sweep the warp runs.  (Warps beyond the rows of a short listed tile hold zeros with inactive flags and
+  // run the profile loop on them: a third, barrier-only loop — or any branch around the half-sweeps — makes ptxas
+  // shuffle ~20 more registers per half-sweep of the profile loop, 12 % on the 8-row kernel.)
+  // (kWallModes = false compiles modes 3 / 4 out: with them ptxas shuffles ~20 more registers per half-sweep of the
+  // profile loop — 12 % on the 8-row kernel — and the pass is paced by the obstacle tiles, not the wall tiles.)
+  const int sweep_mode = irr_rows == 0 ? 0
+                         : kWallModes && (irr_rows & ~3u) == 0 ? 3
+                         : kWallModes && (irr_rows & ~(3u << (RY - 2))) == 0 ? 4 : 1;
   const u64 o2 = pk(a.o, a.o);
   __syncthreads();
   if (tl && threadIdx.x == 0) tl[1] = globaltimer();
@@ -662,7 +666,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
           __syncthreads();
         }
       }
-    } else if (sweep_mode == 3) {
+    } else if (kWallModes && sweep_mode == 3) {
       for (int it = 0; it < its; it++) {
         if (q == 0) {
           half_sweep<RY, 0, 3, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
@@ -676,7 +680,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
           __syncthreads();
         }
       }
-    } else if (sweep_mode == 4) {
+    } else if (kWallModes && sweep_mode == 4) {
       for (int it = 0; it < its; it++) {
         if (q == 0) {
           half_sweep<RY, 0, 4, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
@@ -689,11 +693,6 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
           half_sweep<RY, 0, 4, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
           __syncthreads();
         }
-      }
-    } else {
-      for (int it = 0; it < its; it++) {
-        __syncthreads();
-        __syncthreads();
       }
     }
     if (rtl) rtl[1] = globaltimer();
@@ -1603,7 +1602,8 @@ int tiled_prepare(Sim* s, int iterations) {
       // one timed run of a candidate (ms), or a negative value on failure
       auto time_once = [&](const Cand& c) -> float {
         cudaEventRecord(e0, s->stream);
-        int r = run_passes(s, c.variant, c.T, iterations, 1.0f, false, false, -1, 0, c.resident != 0);
+        // (a linked slab's candidates are timed over the row windows its passes will sweep: s->tune_depth)
+        int r = run_passes(s, c.variant, c.T, iterations, 1.0f, false, false, c.resident ? -1 : s->tune_depth, 0, c.resident != 0);
         cudaEventRecord(e1, s->stream);
         if (r != SAYAL_OK || cudaEventSynchronize(e1) != cudaSuccess) return -1.f;
         float ms = 0.f;
@@ -1702,7 +1702,11 @@ int tiled_prepare(Sim* s, int iterations) {
 // will use: the same pass list as run_passes.  ghost_depth: exact ghost rows at the start of a deep-halo call;
 // ignored in push mode (s->push_active).
 int tiled_prepare_windows(Sim* s, int iterations, int ghost_depth) {
+  // the tuner times its candidates over the windows the passes will really sweep (whole-array passes take the tile
+  // list with its cut tiles, windows the regular grid: a plan that wins on one can lose on the other)
+  s->tune_depth = push_sides_of(s) ? s->slab_halo : ghost_depth;
   int r = tiled_prepare(s, iterations);
+  s->tune_depth = -1;
   const int sides = push_sides_of(s);
   if (r != SAYAL_OK || iterations <= 0 || (ghost_depth < 0 && !sides)) return r;
   static thread_local PassPlan plans[kMaxPasses];

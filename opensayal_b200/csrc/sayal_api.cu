@@ -190,6 +190,7 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
   s->proj_depth = -1;
   s->order_tiles = 1;
   s->split_tiles = 1;
+  s->tune_depth = -1;
   s->advect_kernel = 2;
   s->overlap_exchange = 1;
   s->slab_push = 1;

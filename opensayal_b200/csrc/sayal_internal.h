@@ -197,6 +197,7 @@ struct Sim {
   int order_tiles;        // option (default 1)
   static constexpr int kMaxOrders = 256;
   struct TileOrder { int variant, it, row_lo, row_hi, edge_first; int* order; int n_descs; } orders[kMaxOrders];  // edge_first -1: `order` holds a tile list (TileDesc)
+  int tune_depth;         // ghost depth the plan tuner times its candidates with (-1: whole-array passes)
   int split_tiles;        // option (default 1): whole-domain passes run over an explicit tile list (projection_pack.cu)
   int n_orders;
   // CUDA graph cache for sayal_run: one single-step graph per starting buffer parity, with the

@@ -13,7 +13,7 @@ SAYAL_BENCH_SKIP_STRONG=1 python bench.py --steps 3 --warmup 3 --skip-cpu-baseli
 T=$(python -c "import json;print(json.load(open('gpurun_out/${tag}_plan.json'))['plan']['temporal_block'])")
 R=$(python -c "import json;print(json.load(open('gpurun_out/${tag}_plan.json'))['plan']['tile_rows_per_warp'])")
 echo "plan: T=$T rows=$R"
-export SAYAL_BENCH_SKIP_STRONG=1
+export SAYAL_BENCH_SKIP_STRONG=1 SAYAL_BENCH_NO_GATE=1
 export SAYAL_AUTOTUNE=0 SAYAL_TEMPORAL_BLOCK=$T SAYAL_TILE_ROWS=$R
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --skip-cpu-baseline > gpurun_out/${tag}_launches.log 2>&1

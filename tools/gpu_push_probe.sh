@@ -6,7 +6,5 @@ mkdir -p gpurun_out
 {
 echo "== marginals, deep halo 118"; SAYAL_SLAB_PUSH=0 timeout 300 $TR tools/slab_marginal.py --halos 118 2>/dev/null | grep "^N="
 echo "== marginals, deep halo 118, rows 8 T 8 forced"; SAYAL_TILE_ROWS=8 SAYAL_TEMPORAL_BLOCK=8 SAYAL_SLAB_PUSH=0 timeout 300 $TR tools/slab_marginal.py --halos 118 2>/dev/null | grep "^N="
-echo "== marginals, deep halo 118, T 10 forced"; SAYAL_TEMPORAL_BLOCK=10 SAYAL_SLAB_PUSH=0 timeout 300 $TR tools/slab_marginal.py --halos 118 2>/dev/null | grep "^N="
-echo "== marginals, deep halo 118, no shrink"; SAYAL_SHRINK_WINDOW=0 SAYAL_SLAB_PUSH=0 timeout 300 $TR tools/slab_marginal.py --halos 118 2>/dev/null | grep "^N="
-echo "== timeline deep"; SAYAL_SLAB_PUSH=0 timeout 300 $TR tools/push_timeline.py --halo 118 2>/dev/null | grep -v "^\*\|OMP\|^$"
-} 2>&1 | tee gpurun_out/push_probe3_n$N.log
+echo "== stage times (eager)"; timeout 300 $TR tools/slab_stage_times.py 2>/dev/null | grep "^rank"
+} 2>&1 | tee gpurun_out/push_probe4_n$N.log
