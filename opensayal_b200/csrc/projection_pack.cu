@@ -1598,6 +1598,7 @@ int tiled_prepare(Sim* s, int iterations) {
       if (save_p) cudaMemcpyAsync(spres, s->p, bytes, cudaMemcpyDeviceToDevice, s->stream);
       int64_t launches = s->launches;
       int parity = s->parity;
+      const int orders_before = s->n_orders;  // the candidates' issue orders / tile lists are dropped after the tuning
       float *u0 = s->u, *v0 = s->v, *ub0 = s->u_buf, *vb0 = s->v_buf;
       // one timed run of a candidate (ms), or a negative value on failure
       auto time_once = [&](const Cand& c) -> float {
@@ -1651,6 +1652,12 @@ int tiled_prepare(Sim* s, int iterations) {
           if (cands[c].ms <= limit && cands[c].cost < cands[best].cost) best = c;
       }
       timed = true;
+      // the cache of issue orders holds one entry per geometry a candidate swept (a slab's row windows: one per pass):
+      // keep only what was there before — the chosen plan's entries are rebuilt right after (below / by the caller)
+      cudaStreamSynchronize(s->stream);
+      for (int k = orders_before; k < s->n_orders; k++)
+        if (s->orders[k].order) cudaFree(s->orders[k].order);
+      s->n_orders = orders_before;
       // restore state and bookkeeping: tuning is invisible
       s->u = u0; s->v = v0; s->u_buf = ub0; s->v_buf = vb0;
       s->parity = parity;
