@@ -258,6 +258,12 @@ int sayal_plan_log(sayal_sim* sim, char* buf, int32_t capacity);
 /* Profiling only (option "debug_timeline" = 1): per-CTA timestamps of the last projection pass, 5 int64 per tile
  * {entry, tile loaded, sweeps done, stores issued (globaltimer ns), SM id}. */
 int sayal_debug_timeline(sayal_sim* sim, int64_t* host_dst, int32_t max_tiles, int32_t* n_tiles);
+/* Diagnostics: the explicit tile list the current plan's whole-array passes of `iterations_per_pass` iterations run
+ * over (option "split_tiles": obstacle tiles cut in two, last tile row aligned to the bottom wall, sorted by cost), 5
+ * int32 per tile: first column, first row held, end of the rows held, first row written, end of the rows written; the
+ * tile writes columns [X0 == 0 ? 0 : X0 + halo_x, X0 + 128 >= pitch ? pitch : X0 + 128 - halo_x).  *n_tiles = 0 when no
+ * such list has been built (plan not chosen yet, option off, or the pass uses the regular grid). */
+int sayal_debug_tile_list(sayal_sim* sim, int32_t iterations_per_pass, int32_t* out, int32_t capacity, int32_t* n_tiles);
 /* Profiling only (option "debug_events" = 1, eager sayal_step): milliseconds from the start of the last step to its
  * stage boundaries — [1] projection done, [2] velocity advected, [3] / [4] edge rows of the velocity / smoke advected
  * (linked slabs), [5] end-of-step exchange done (aux stream), [6] interior rows advected, [7] step done; -1 = not

@@ -157,6 +157,7 @@ SYMBOLS = [
     ("sayal_debug_timeline", C.c_int, [_simp, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     ("sayal_debug_link_words", C.c_int, [_simp, C.c_void_p]),
     ("sayal_debug_stage_times", C.c_int, [_simp, C.c_void_p, C.c_int32]),
+    ("sayal_debug_tile_list", C.c_int, [_simp, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     ("sayal_stream_delay", C.c_int, [_simp, C.c_int64]),
     ("sayal_stream_hold", C.c_int, [_simp]),
     ("sayal_stream_release", C.c_int, [_simp]),

@@ -1751,6 +1751,26 @@ int tiled_debug_pass_plans(int pitch, int local_rows, int own_lo, int own_hi, in
   return n;
 }
 
+// Diagnostics: the explicit tile list of the plan's passes of `it` iterations over the whole array, as 5 int32 per tile
+// (X0, Y0, y_end, vy0, vy1), in issue order; returns the number of tiles, 0 if no such list has been built, -1 on error.
+int tiled_debug_tile_list(Sim* s, int it, int32_t* out, int capacity) {
+  for (int k = 0; k < s->n_orders; k++) {
+    const Sim::TileOrder& o = s->orders[k];
+    if (o.edge_first != -1 || o.variant != s->plan_variant || o.it != it || o.row_lo != 0 || o.row_hi != s->g.local_rows) continue;
+    const int n = o.n_descs < capacity ? o.n_descs : capacity;
+    std::vector<TileDesc> host(n);
+    if (cudaStreamSynchronize(s->stream) != cudaSuccess ||
+        cudaMemcpy(host.data(), o.order, n * sizeof(TileDesc), cudaMemcpyDeviceToHost) != cudaSuccess)
+      return -1;
+    for (int t = 0; t < n; t++) {
+      const int32_t row[5] = {host[t].X0, host[t].Y0, host[t].y_end, host[t].vy0, host[t].vy1};
+      for (int c = 0; c < 5; c++) out[5 * t + c] = row[c];
+    }
+    return o.n_descs;
+  }
+  return 0;
+}
+
 int launch_projection_tiled(Sim* s, int iterations, float d_t) {
   int r = tiled_prepare(s, iterations);
   if (r != SAYAL_OK) return r;

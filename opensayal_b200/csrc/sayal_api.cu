@@ -1151,6 +1151,16 @@ int sayal_stream_delay(sayal_sim* sim, int64_t microseconds) {
   return SAYAL_OK;
 }
 
+int sayal_debug_tile_list(sayal_sim* sim, int32_t iterations_per_pass, int32_t* out, int32_t capacity, int32_t* n_tiles) {
+  if (!sim || !out || !n_tiles || capacity < 0) return set_error(SAYAL_EINVAL, "sayal_debug_tile_list: bad argument");
+  Sim* s = S(sim);
+  CUDA_TRY(cudaSetDevice(s->device));
+  int n = tiled_debug_tile_list(s, iterations_per_pass, out, capacity);
+  if (n < 0) return set_error(SAYAL_ECUDA, "sayal_debug_tile_list: copy failed");
+  *n_tiles = n;
+  return SAYAL_OK;
+}
+
 int sayal_debug_stage_times(sayal_sim* sim, float* ms_out, int32_t capacity) {
   if (!sim || !ms_out) return set_error(SAYAL_EINVAL, "sayal_debug_stage_times: null argument");
   Sim* s = S(sim);

@@ -288,6 +288,7 @@ int launch_projection_tiled(Sim* s, int iterations, float d_t);
 int tiled_max_temporal_block();
 int tiled_debug_pass_plans(int pitch, int local_rows, int own_lo, int own_hi, int rows_per_warp, int T, int iterations,
                            int ghost_depth, int32_t* out, int capacity);  // host only; 15 int32 per pass, see sayal.h
+int tiled_debug_tile_list(Sim* s, int it, int32_t* out, int capacity);  // the plan's explicit tile list (sayal_debug_tile_list)
 int tiled_push_temporal_block(int iterations, int halo);  // push mode: the T every rank of a chain uses
 int preload_basic();   // each file's kernels, loaded at sayal_create (see tiled_preload)
 int preload_advect();

@@ -352,6 +352,13 @@ class Fluid:
         check(self._lib.sayal_debug_timeline(self._sim, out.ctypes.data_as(C.c_void_p), max_tiles, C.byref(n)))
         return out[: n.value]
 
+    def debug_tile_list(self, iterations_per_pass: int, capacity: int = 4096) -> np.ndarray:
+        """Diagnostics: (tiles, 5) int32 {X0, Y0, y_end, vy0, vy1} of the plan's explicit tile list (may be empty)."""
+        out = np.zeros((capacity, 5), dtype=np.int32)
+        n = C.c_int32()
+        check(self._lib.sayal_debug_tile_list(self._sim, int(iterations_per_pass), out.ctypes.data_as(C.c_void_p), capacity, C.byref(n)))
+        return out[: n.value]
+
     def debug_stage_times(self) -> np.ndarray:
         """Profiling only (option debug_events): ms from the start of the last eager step to its stage boundaries."""
         out = np.zeros(10, dtype=np.float32)

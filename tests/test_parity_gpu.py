@@ -188,6 +188,41 @@ def test_listed_tiles_cut_and_shifted_change_no_bit(height, cy, radius, rows, T)
     assert_same(gpu, cpu, what="listed tiles, steps")
 
 
+@pytest.mark.parametrize("width,height,radius", [(1920, 1080, 36.0), (520, 470, 60.0), (700, 333, 45.0)])
+def test_tile_list_partitions_the_domain(width, height, radius):
+    """Covering invariants of the explicit tile list a whole-domain pass runs over (sayal_debug_tile_list): the written
+    rectangles partition the array exactly (every cell written by one tile), every tile holds its written rows plus a
+    halo of 2 T rows wherever it has a neighbour, at most 16 x rows-per-warp rows, and a disc this large gets cut."""
+    cfg = baseline_config(1, width=width, height=height)
+    cfg["sim.obstacle.radius"] = radius
+    cfg["sim.obstacle.center_x"], cfg["sim.obstacle.center_y"] = width // 2, height // 2
+    gpu = Fluid(cfg)
+    gpu.set_option("resident", 0)
+    gpu.set_option("autotune", 0)
+    T, rows_per_warp = 8, 12
+    gpu.set_option("temporal_block", T)
+    gpu.set_option("tile_rows_per_warp", rows_per_warp)
+    gpu.stage_projection(T, 0.05)  # one pass of T iterations builds the list
+    tiles = gpu.debug_tile_list(T)
+    assert len(tiles) > 0
+    pitch = gpu.get_option("pitch")
+    halo_y, halo_x, TW, TH = 2 * T, (2 * T + 3) & ~3, 128, 16 * rows_per_warp
+    cover = np.zeros((height, pitch), dtype=np.int32)
+    for X0, Y0, y_end, vy0, vy1 in tiles:
+        vx0 = 0 if X0 == 0 else X0 + halo_x
+        vx1 = pitch if X0 + TW >= pitch else X0 + TW - halo_x
+        cover[vy0:vy1, vx0:vx1] += 1
+        assert Y0 <= vy0 < vy1 <= y_end <= min(Y0 + TH, height) and X0 % 4 == 0
+        assert vy0 == 0 or vy0 - Y0 >= halo_y          # a tile edge with a neighbour keeps its halo
+        assert vy1 == height or y_end - vy1 >= halo_y
+    assert (cover == 1).all()
+    regular = -(-(pitch - TW) // (TW - 2 * halo_x)) + 1
+    assert len(tiles) >= regular  # at least one tile row
+    base_rows = 1 if height <= TH else -(-(height - TH) // (TH - 2 * halo_y)) + 1
+    assert len(tiles) > regular * base_rows  # the disc's tiles were cut in two
+    gpu.close()
+
+
 def test_projection_with_pressure_and_range():
     cfg = baseline_config(0)
     gpu, cpu = pair(cfg)
