@@ -14,14 +14,15 @@
 //   * Columns (1,3) need u of the next lane's column 0: one __shfl_down brings it, one __shfl_up returns the
 //     updated face.  Vertically adjacent warps share one row of v faces through shared memory (colour-split
 //     float2 slots, conflict-free), one barrier per half-sweep.
-//   * Cell masks without branches: the face updates of apply_projection_at (fluid.cu:247-261) are written as
-//     fma(e, m, face) with m in {+-1, 0} and the divide by total_s as a multiply by inv in {0, 1, 1/2, 1/3, 1/4}
+//   * Cell masks without branches: on the lanes' common path the face updates of apply_projection_at (fluid.cu:247-261)
+//     are fma(e, m, face) with m in {+-1, 0} and the divide by total_s is a multiply by inv in {0, 1, 1/2, 1/3, 1/4}
 //     (inv = 0 switches a cell off).  Each lane keeps ONE "profile" of these multipliers (the flags of its
 //     reference row) in registers; every row whose flags equal the profile — all rows of an open tile, and all
 //     rows of a tile that only touches the left/right wall — costs exactly the same instructions as an open
-//     row.  Rows that differ (top/bottom wall, obstacle rim) fetch their multipliers from a 256-entry
-//     shared-memory table indexed by the two cells' face nibbles.  fma(e, +-1, x) == x +- e and
-//     fma(e, 0, x) == x exactly, so no bit changes with respect to the branchy form.
+//     row.  Warps with rows that differ (top/bottom wall, obstacle rim) run the "bits" path: per row one byte of face
+//     bits and inv from a 256-entry shared-memory table, the four face updates as predicated scalar adds (three
+//     registers per row in flight instead of ten multipliers: these warps are latency-bound and pace the pass).
+//     fma(e, +-1, x) == x +- e exactly and a closed face is not touched, like the reference's `if`.
 //   * Tiles overlap by a halo of 2T cells (rounded up to 4 in x).  Errors from the missing neighbours travel
 //     one cell per half-sweep, so after 2T half-sweeps everything at least 2T cells inside the tile is exactly
 //     what the global sweep order produces; only that part is written, to the OTHER buffer (ping-pong).
@@ -44,7 +45,6 @@ namespace {
 typedef unsigned long long u64;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int TW = 128;  // tile width: 32 lanes x 4 cells
-constexpr bool kWallModes = false;  // half_sweep modes 3 / 4 (see the kernel)
 
 // ---- packed fp32 pairs (element 0 = low register) ------------------------------------------------------
 __device__ __forceinline__ u64 pk(float lo, float hi) {
@@ -88,9 +88,9 @@ __device__ __forceinline__ u64 lds64(const float* p) {
 }
 __device__ __forceinline__ void sts64(float* p, u64 v) { *reinterpret_cast<float2*>(p) = make_float2(lo(v), hi(v)); }
 
-// The multipliers of one pair of cells.  nR / nT are stored negated: face -= e  ==  fma(e, -1, face).
+// The profile multipliers of one pair of cells.  nR is stored negated: face -= e  ==  fma(e, -1, face).
 struct Mult {
-  u64 inv, mL, nR, mB, nT;
+  u64 inv, mL, nR;
 };
 
 __device__ __forceinline__ float inv_of(unsigned nibble) {
@@ -100,37 +100,26 @@ __device__ __forceinline__ float inv_of(unsigned nibble) {
 __device__ __forceinline__ float bit_pos(unsigned nibble, unsigned bit) { return (nibble & bit) ? 1.0f : 0.0f; }
 __device__ __forceinline__ float bit_neg(unsigned nibble, unsigned bit) { return (nibble & bit) ? -1.0f : 0.0f; }
 
-// Shared-memory table entry (48 B): multipliers of the cell pair with face nibbles (a, c).
-struct __align__(16) LutEntry {
-  float inv_a, inv_c, mL_a, mL_c;
-  float nR_a, nR_c, mB_a, mB_c;
-  float nT_a, nT_c, pad0, pad1;
-};
-
-__device__ __forceinline__ void lut_fill(LutEntry* e, unsigned a, unsigned c) {
-  e->inv_a = inv_of(a); e->inv_c = inv_of(c);
-  e->mL_a = bit_pos(a, FL_L); e->mL_c = bit_pos(c, FL_L);
-  e->nR_a = bit_neg(a, FL_R); e->nR_c = bit_neg(c, FL_R);
-  e->mB_a = bit_pos(a, FL_B); e->mB_c = bit_pos(c, FL_B);
-  e->nT_a = bit_neg(a, FL_T); e->nT_c = bit_neg(c, FL_T);
-  e->pad0 = e->pad1 = 0.f;
+// Rows that differ from the lane's profile (walls, an obstacle's rim) carry, per colour, the face nibbles of their
+// two cells as one byte (cell a low, cell c high: FL_L, FL_R, FL_B, FL_T each) and fetch 1 / total_s of both cells from
+// a 256-entry table in shared memory.  The four face updates of apply_projection_at (fluid.cu:247-261) are then
+// PREDICATED scalar adds on that byte: a closed face is simply not touched, like the reference's `if`.  (The first
+// generation multiplied by {+-1, 0} fetched from a 48-byte table entry: ten registers of multipliers per row in
+// flight, so ptxas could overlap hardly any rows and these warps — bound by the latency of a row's chain, not by issue
+// slots — paced every pass.  Byte + two floats: three registers per row.)
+__device__ __forceinline__ unsigned pair_index(unsigned fl, int c) {
+  unsigned t = (fl >> (8 * c)) & 0x000f000fu;  // CASE 0 -> flag bytes 0 and 2, CASE 1 -> bytes 1 and 3
+  return (t | (t >> 12)) & 0xffu;
 }
-
-// byte offset of the table entry of a row's (a, c) pair: CASE 0 -> flag bytes 0 and 2, CASE 1 -> bytes 1 and 3
-__device__ __forceinline__ unsigned pair_offset(unsigned fl, int c) {
-  unsigned t = (fl >> (8 * c)) & 0x000f000fu;
-  return ((t | (t >> 12)) & 0xffu) * (unsigned)sizeof(LutEntry);
+__device__ __forceinline__ float add_if(float x, float e, unsigned bits, unsigned bit) {
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\t@p add.rn.f32 %0, %0, %1;\n\t}"
+      : "+f"(x) : "f"(e), "r"(bits), "r"(bit));
+  return x;
 }
-
-__device__ __forceinline__ Mult lut_load(const LutEntry* lut, unsigned byte_offset) {
-  const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(lut) + byte_offset);
-  float4 a = q[0], b = q[1];
-  float2 c = *reinterpret_cast<const float2*>(q + 2);
-  Mult m;
-  m.inv = pk(a.x, a.y); m.mL = pk(a.z, a.w);
-  m.nR = pk(b.x, b.y); m.mB = pk(b.z, b.w);
-  m.nT = pk(c.x, c.y);
-  return m;
+__device__ __forceinline__ float sub_if(float x, float e, unsigned bits, unsigned bit) {
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\t@p sub.rn.f32 %0, %0, %1;\n\t}"
+      : "+f"(x) : "f"(e), "r"(bits), "r"(bit));
+  return x;
 }
 
 // In-pass push of a linked y-slab (no reference equivalent: OpenSayal is single-GPU).  A pass of `it`
@@ -324,7 +313,8 @@ __device__ __forceinline__ void pressure_add(float* pp, u64 e, const PMul& pm) {
   sts64(pp, fma2(mul2(mul2(e, pm.density), pm.hf), pm.inv_dt, lds64(pp)));
 }
 
-template <int C, bool MASKED, bool PRESSURE>
+// Profile rows: the lane's multipliers (inv, mL, nR) in registers, both v faces open.
+template <int C, bool PRESSURE>
 __device__ __forceinline__ void row_step(u64& U02, u64& U13, u64& vb, u64& vt, const Mult& m, u64 o2, int lane, float* pp,
                                          const PMul& pm) {
   if (C == 0) {
@@ -333,13 +323,8 @@ __device__ __forceinline__ void row_step(u64& U02, u64& U13, u64& vb, u64& vt, c
     if (PRESSURE) pressure_add(pp, e, pm);
     U02 = fma2(e, m.mL, U02);
     U13 = fma2(e, m.nR, U13);
-    if (MASKED) {
-      vb = fma2(e, m.mB, vb);
-      vt = fma2(e, m.nT, vt);
-    } else {
-      vb = add2(vb, e);
-      vt = sub2(vt, e);
-    }
+    vb = add2(vb, e);
+    vt = sub2(vt, e);
   } else {
     // right faces of columns 1 and 3: own column 2 and the next lane's column 0
     float un = __shfl_down_sync(FULL, lo(U02), 1);
@@ -349,29 +334,51 @@ __device__ __forceinline__ void row_step(u64& U02, u64& U13, u64& vb, u64& vt, c
     if (PRESSURE) pressure_add(pp, e, pm);
     U13 = fma2(e, m.mL, U13);
     uR = fma2(e, m.nR, uR);
-    if (MASKED) {
-      vb = fma2(e, m.mB, vb);
-      vt = fma2(e, m.nT, vt);
-    } else {
-      vb = add2(vb, e);
-      vt = sub2(vt, e);
-    }
+    vb = add2(vb, e);
+    vt = sub2(vt, e);
     // the updated face of the next lane's column 0 travels back; lane 0 has no left neighbour in the tile
     float back = __shfl_up_sync(FULL, hi(uR), 1);
     U02 = pk(lane == 0 ? lo(U02) : back, lo(uR));
   }
 }
 
+// Rows off the profile: inv = 1 / total_s of the two cells (0 switches a cell off), bits = their face nibbles
+// (cell a: bits 0..3, cell c: bits 4..7); every face update is a predicated scalar add.
+template <int C, bool PRESSURE>
+__device__ __forceinline__ void row_step_bits(u64& U02, u64& U13, u64& vb, u64& vt, u64 inv, unsigned bits, u64 o2, int lane,
+                                              float* pp, const PMul& pm) {
+  u64 uR = 0;
+  u64 d;
+  if (C == 0) {
+    d = sub2(add2(sub2(U13, U02), vt), vb);
+  } else {
+    float un = __shfl_down_sync(FULL, lo(U02), 1);
+    uR = pk(hi(U02), un);
+    d = sub2(add2(sub2(uR, U13), vt), vb);
+  }
+  const u64 e = mul2(o2, mul2(d, inv));
+  if (PRESSURE) pressure_add(pp, e, pm);
+  const float ea = lo(e), ec = hi(e);
+  u64& left = C == 0 ? U02 : U13;   // the left faces of the two cells
+  u64& right = C == 0 ? U13 : uR;   // their right faces
+  left = pk(add_if(lo(left), ea, bits, FL_L), add_if(hi(left), ec, bits, FL_L << 4));
+  right = pk(sub_if(lo(right), ea, bits, FL_R), sub_if(hi(right), ec, bits, FL_R << 4));
+  vb = pk(add_if(lo(vb), ea, bits, FL_B), add_if(hi(vb), ec, bits, FL_B << 4));
+  vt = pk(sub_if(lo(vt), ea, bits, FL_T), sub_if(hi(vt), ec, bits, FL_T << 4));
+  if (C == 1) {
+    float back = __shfl_up_sync(FULL, hi(uR), 1);
+    U02 = pk(lane == 0 ? lo(U02) : back, lo(uR));
+  }
+}
+
 // One half-sweep over the RY rows of this warp.  Q0 = case of row 0; the case alternates with the row.
-// MODE 0: every row uses the lane's profile multipliers.  MODE 1 (a warp with rows that differ from the profile, e.g.
-// an obstacle's rim): every row fetches its multipliers from the table; s_off holds, per row, the two cases' byte
-// offsets into it (16 bits each).  MODE 3 / 4: only the warp's first / last two rows differ (the rows at the top /
-// bottom wall): those two take the table path, the others the profile path — decided at compile time per unrolled
-// row, so there is no per-row branch in any mode (a branch per row keeps ptxas from interleaving the rows).
+// MODE 0: every row uses the lane's profile multipliers.  MODE 1 (a warp with rows that differ from the profile: walls,
+// an obstacle's rim): every row takes the bits path; s_idx holds, per row, the two cases' table indices (16 bits each).
+// No per-row branch in either mode (a branch per row keeps ptxas from interleaving the rows).
 template <int RY, int Q0, int MODE, bool PRESSURE>
 __device__ __forceinline__ void half_sweep(u64 (&U02)[RY], u64 (&U13)[RY], u64 (&V02)[RY - 1], u64 (&V13)[RY - 1],
                                            const Mult (&prof)[2], u64 o2, int lane, float* sv_top, float* sv_bot,
-                                           const unsigned* s_off, const LutEntry* lut, float* sp_warp,
+                                           const unsigned* s_idx, const float2* inv_tab, float* sp_warp,
                                            const PMul& pm) {
 #pragma unroll
   for (int r = 0; r < RY; r++) {
@@ -382,14 +389,15 @@ __device__ __forceinline__ void half_sweep(u64 (&U02)[RY], u64 (&U13)[RY], u64 (
     else vt = c ? V13[r - 1] : V02[r - 1];
     if (r == RY - 1) vb = lds64(sv_bot + 64 * c);
     else vb = c ? V13[r] : V02[r];
-    if (MODE == 1 || (MODE == 3 && r < 2) || (MODE == 4 && r >= RY - 2)) {
-      unsigned word = s_off[r * 32];
-      Mult m = lut_load(lut, c ? (word >> 16) : (word & 0xffffu));
-      if (c == 0) row_step<0, true, PRESSURE>(U02[r], U13[r], vb, vt, m, o2, lane, pp, pm);
-      else row_step<1, true, PRESSURE>(U02[r], U13[r], vb, vt, m, o2, lane, pp, pm);
+    if (MODE == 1) {
+      const unsigned word = s_idx[r * 32];
+      const unsigned bits = c ? (word >> 16) : (word & 0xffffu);
+      const u64 inv = lds64(reinterpret_cast<const float*>(inv_tab + bits));
+      if (c == 0) row_step_bits<0, PRESSURE>(U02[r], U13[r], vb, vt, inv, bits, o2, lane, pp, pm);
+      else row_step_bits<1, PRESSURE>(U02[r], U13[r], vb, vt, inv, bits, o2, lane, pp, pm);
     } else {
-      if (c == 0) row_step<0, false, PRESSURE>(U02[r], U13[r], vb, vt, prof[0], o2, lane, pp, pm);
-      else row_step<1, false, PRESSURE>(U02[r], U13[r], vb, vt, prof[1], o2, lane, pp, pm);
+      if (c == 0) row_step<0, PRESSURE>(U02[r], U13[r], vb, vt, prof[0], o2, lane, pp, pm);
+      else row_step<1, PRESSURE>(U02[r], U13[r], vb, vt, prof[1], o2, lane, pp, pm);
     }
     if (r == 0) sts64(sv_top + 64 * c, vt);
     else if (c) V13[r - 1] = vt;
@@ -418,7 +426,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   // shared v rows: sv[0] is the v row above the tile (read-only halo), sv[w+1] is the last row of warp w.
   // Layout per row: [columns (0,2): 64 floats][columns (1,3): 64 floats]; lane l owns float2 at 2l of each.
   __shared__ __align__(16) float sv[NW + 1][128];
-  __shared__ LutEntry lut[256];
+  __shared__ float2 inv_tab[256];  // 1 / total_s of the two cells of a face-nibble pair (bits path of half_sweep)
   __shared__ unsigned s_off_all[NW][RY][32];
 
   const Grid& g = a.g;
@@ -446,7 +454,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
     tl[4] = smid;
   }
 
-  if (threadIdx.x < 256) lut_fill(&lut[threadIdx.x], threadIdx.x & 15u, threadIdx.x >> 4);
+  if (threadIdx.x < 256) inv_tab[threadIdx.x] = make_float2(inv_of(threadIdx.x & 15u), inv_of(threadIdx.x >> 4));
   // Programmatic dependent launch: let the next pass's CTAs be scheduled as SMs drain, and do not read what the
   // previous kernel wrote before it has completed.  Both are no-ops for a plain launch.
   asm volatile("griddepcontrol.launch_dependents;");
@@ -586,7 +594,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
 #pragma unroll
   for (int r = 0; r < RY; r++) {
     if (__any_sync(FULL, fl[r] != pf)) irr_rows |= 1u << r;
-    s_off[r * 32] = pair_offset(fl[r], 0) | (pair_offset(fl[r], 1) << 16);
+    s_off[r * 32] = pair_index(fl[r], 0) | (pair_index(fl[r], 1) << 16);
   }
   Mult prof[2];
 #pragma unroll
@@ -595,8 +603,6 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
     prof[c].inv = pk(inv_of(na), inv_of(nc));
     prof[c].mL = pk(bit_pos(na, FL_L), bit_pos(nc, FL_L));
     prof[c].nR = pk(bit_neg(na, FL_R), bit_neg(nc, FL_R));
-    prof[c].mB = 0;
-    prof[c].nT = 0;
   }
   // A profile row must have all its B/T faces open for the unmasked v update to be right; if the middle row is
   // itself next to a horizontal boundary, every row goes through the table.
@@ -612,11 +618,7 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
   // which half_sweep the warp runs.  (Warps beyond the rows of a short listed tile hold zeros with inactive flags and
   // run the profile loop on them: a third, barrier-only loop — or any branch around the half-sweeps — makes ptxas
   // shuffle ~20 more registers per half-sweep of the profile loop, 12 % on the 8-row kernel.)
-  // (kWallModes = false compiles modes 3 / 4 out: with them ptxas shuffles ~20 more registers per half-sweep of the
-  // profile loop — 12 % on the 8-row kernel — and the pass is paced by the obstacle tiles, not the wall tiles.)
-  const int sweep_mode = irr_rows == 0 ? 0
-                         : kWallModes && (irr_rows & ~3u) == 0 ? 3
-                         : kWallModes && (irr_rows & ~(3u << (RY - 2))) == 0 ? 4 : 1;
+  const int sweep_mode = irr_rows == 0 ? 0 : 1;
   const u64 o2 = pk(a.o, a.o);
   __syncthreads();
   if (tl && threadIdx.x == 0) tl[1] = globaltimer();
@@ -641,56 +643,28 @@ __global__ void __launch_bounds__(NW * 32, 1) projection_pack_kernel(PackArgs a)
     if (sweep_mode == 0) {
       for (int it = 0; it < its; it++) {
         if (q == 0) {
-          half_sweep<RY, 0, 0, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          half_sweep<RY, 0, 0, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, inv_tab, sp_warp, pm);
           __syncthreads();
-          half_sweep<RY, 1, 0, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          half_sweep<RY, 1, 0, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, inv_tab, sp_warp, pm);
           __syncthreads();
         } else {
-          half_sweep<RY, 1, 0, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          half_sweep<RY, 1, 0, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, inv_tab, sp_warp, pm);
           __syncthreads();
-          half_sweep<RY, 0, 0, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          half_sweep<RY, 0, 0, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, inv_tab, sp_warp, pm);
           __syncthreads();
         }
       }
     } else if (sweep_mode == 1) {
       for (int it = 0; it < its; it++) {
         if (q == 0) {
-          half_sweep<RY, 0, 1, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          half_sweep<RY, 0, 1, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, inv_tab, sp_warp, pm);
           __syncthreads();
-          half_sweep<RY, 1, 1, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-          __syncthreads();
-        } else {
-          half_sweep<RY, 1, 1, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-          __syncthreads();
-          half_sweep<RY, 0, 1, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-          __syncthreads();
-        }
-      }
-    } else if (kWallModes && sweep_mode == 3) {
-      for (int it = 0; it < its; it++) {
-        if (q == 0) {
-          half_sweep<RY, 0, 3, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-          __syncthreads();
-          half_sweep<RY, 1, 3, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          half_sweep<RY, 1, 1, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, inv_tab, sp_warp, pm);
           __syncthreads();
         } else {
-          half_sweep<RY, 1, 3, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          half_sweep<RY, 1, 1, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, inv_tab, sp_warp, pm);
           __syncthreads();
-          half_sweep<RY, 0, 3, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-          __syncthreads();
-        }
-      }
-    } else if (kWallModes && sweep_mode == 4) {
-      for (int it = 0; it < its; it++) {
-        if (q == 0) {
-          half_sweep<RY, 0, 4, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-          __syncthreads();
-          half_sweep<RY, 1, 4, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-          __syncthreads();
-        } else {
-          half_sweep<RY, 1, 4, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
-          __syncthreads();
-          half_sweep<RY, 0, 4, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, lut, sp_warp, pm);
+          half_sweep<RY, 0, 1, PRESSURE>(U02, U13, V02, V13, prof, o2, lane, sv_top, sv_bot, s_off, inv_tab, sp_warp, pm);
           __syncthreads();
         }
       }
