@@ -246,10 +246,13 @@ int sayal_path_lines(sayal_sim* sim, const sayal_visual* v, float d_t, int32_t* 
  * blocked), "temporal_block" (iterations per pass, 0 = choose), "tile_rows_per_warp" (0 = choose, 8/10/12),
  * "autotune" (time candidate tile plans on first use), "use_graph", "use_pdl", "fuse_forces" / "fuse_extrapolation"
  * (fold those stages into the first / last projection pass), "order_tiles" (issue expensive tiles first),
- * "advect_kernel", "advect_margin", "overlap_exchange", "slab_push" (linked slabs: passes push their own edge rows);
- * "debug_timeline" / "debug_skip" are profiling aids (the latter leaves stages out and does change results).  get:
- * the same plus "plan_temporal_block", "plan_rows_per_warp", "push_mode", "halo_overflow", "link_error", "pitch",
- * "local_rows", "own_lo", "own_hi".  No other option changes results. */
+ * "split_tiles" (whole-domain passes run over an explicit tile list: obstacle tiles cut in two, sorted by cost),
+ * "resident" (0 = never, 1 = time the resident plans — the whole projection in one cooperative launch — with the
+ * others, 2 = resident plans only), "advect_kernel", "advect_margin", "overlap_exchange", "slab_push" (linked slabs:
+ * passes push their own edge rows); "debug_timeline" / "debug_events" / "debug_skip" are profiling aids (the last
+ * leaves stages out and does change results).  get: the same plus "plan_temporal_block", "plan_rows_per_warp",
+ * "plan_resident", "push_mode", "halo_overflow", "link_error", "pitch", "local_rows", "own_lo", "own_hi".  No other
+ * option changes results. */
 int sayal_set_option(sayal_sim* sim, const char* key, int64_t value);
 int sayal_get_option(sayal_sim* sim, const char* key, int64_t* value);
 /* The candidates the tile-plan tuner timed for the last projection it planned, as text (one "rows T model ms" line
