@@ -506,6 +506,43 @@ def test_large_grid_properties_3840x2160():
     assert mean_div(uu, vv) < 0.25 * mean_div(u, v)
 
 
+def test_batched_and_device_field_io_and_the_stream_gate():
+    """sayal_set_fields / sayal_get_fields (batched, host), sayal_set_field_device / sayal_get_field_device (device
+    buffers in the reference layout, odd width: padded pitch inside) move the same bits as the one-field calls; steps
+    enqueued behind sayal_stream_hold run when sayal_stream_release says so and give the same result."""
+    import torch
+    cfg = Config.defaults(203, 157, **{"fluid.viscosity": 0.0, "sim.wind_tunnel.speed": 60.0})
+    W, H = cfg.c.width, cfg.c.height
+    u, v, sm = synthetic_fields(W, H)
+    a, b = Fluid(cfg), Fluid(cfg)
+    for n, x in (("u", u), ("v", v), ("smoke", sm)):
+        a.set_field(n, x)
+    pinned = {n: torch.from_numpy(x.copy()).pin_memory() for n, x in (("u", u), ("v", v), ("smoke", sm))}
+    b.set_fields_from({n: t.data_ptr() for n, t in pinned.items()})
+    b.sync()
+    for n in ("u", "v", "smoke"):
+        assert np.array_equal(a.get_field(n), b.get_field(n)), n
+    a.run(2)
+    b.stream_hold()          # the two steps wait on the device ...
+    b.run(2)
+    b.stream_release()       # ... until the host opens the gate
+    out = {n: torch.empty((H, W), dtype=torch.float32).pin_memory() for n in ("u", "v", "smoke")}
+    b.get_fields_into({n: t.data_ptr() for n, t in out.items()})
+    for n in ("u", "v", "smoke"):
+        assert np.array_equal(a.get_field(n), out[n].numpy()), n
+    dev = torch.empty((H, W), dtype=torch.float32, device="cuda")
+    a.get_field_device("smoke", dev.data_ptr())
+    a.sync()
+    assert np.array_equal(dev.cpu().numpy(), a.get_field("smoke"))
+    dev.mul_(0.5)
+    torch.cuda.synchronize()
+    a.set_field_device("smoke", dev.data_ptr())
+    a.sync()
+    assert np.array_equal(a.get_field("smoke"), dev.cpu().numpy())
+    a.close()
+    b.close()
+
+
 def test_errors_are_codes_not_exits():
     from opensayal_b200 import SayalError
     cfg = Config.defaults(2, 2)
