@@ -315,6 +315,7 @@ def bench_ours_single(args):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
         "clocks": clocks.summary(),
         "steady_state_ms_per_step_l2_warm": warm_ms,
+        "step_ms": {"min": round(min(step_ms), 4), "median": round(statistics.median(step_ms), 4), "max": round(max(step_ms), 4)},
         "stage_ms": {"projection": proj_ms},
         "strong_16384": strong,
     }
