@@ -1625,6 +1625,11 @@ int tiled_prepare(Sim* s, int iterations) {
         for (int c = 0; c < finalists; c++)
           if (cands[c].ms <= limit && cands[c].cost < cands[best].cost) best = c;
       }
+      // A resident plan needs every SM for itself (cooperative launch) and its timing in isolation flatters it: it
+      // must beat the best multi-pass finalist by 3 % to be chosen.
+      if (cands[best].resident)
+        for (int c = 0; c < finalists; c++)
+          if (!cands[c].resident && cands[c].ms <= cands[best].ms * 1.03f && (cands[best].resident || cands[c].ms < cands[best].ms)) best = c;
       timed = true;
       // the cache of issue orders holds one entry per geometry a candidate swept (a slab's row windows: one per pass):
       // keep only what was there before — the chosen plan's entries are rebuilt right after (below / by the caller)
