@@ -183,6 +183,9 @@ def bench_ours_single(args):
             gate = not os.environ.get("SAYAL_BENCH_NO_GATE")  # under ncu every launch is serialised: a gate would spin to its time-out
             if gate:
                 sim.stream_hold()
+                for _ in range(2):  # untimed: the first step behind the gate finds the GPU ramping up from the one-thread
+                    flush_l2()      # spin (measured: step 0 took 0.22-0.27 ms, every other step 0.178) — same as bench_slabs
+                    sim.run(1)
             for k in range(done, done + chunk):
                 flush_l2()
                 starts[k].record(stream)
@@ -192,7 +195,9 @@ def bench_ours_single(args):
                 sim.stream_release()
             sim.sync()
             done += chunk
-    launches = sim.launch_count - launches0
+    chunks = -(-args.steps // 40)
+    extra = 0 if os.environ.get("SAYAL_BENCH_NO_GATE") else 2 * chunks  # untimed alignment steps behind each gate
+    launches = (sim.launch_count - launches0) * args.steps // (args.steps + extra)  # launches of the timed steps only
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
     ms_per_step = sum(step_ms) / len(step_ms)
     value = cells / (ms_per_step * 1e-3)
@@ -315,7 +320,8 @@ def bench_ours_single(args):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
         "clocks": clocks.summary(),
         "steady_state_ms_per_step_l2_warm": warm_ms,
-        "step_ms": {"min": round(min(step_ms), 4), "median": round(statistics.median(step_ms), 4), "max": round(max(step_ms), 4)},
+        "step_ms": {"min": round(min(step_ms), 4), "median": round(statistics.median(step_ms), 4), "max": round(max(step_ms), 4),
+                    "slowest_step": step_ms.index(max(step_ms))},
         "stage_ms": {"projection": proj_ms},
         "strong_16384": strong,
     }
