@@ -59,9 +59,8 @@ static void free_sim(Sim* s) {
   cudaSetDevice(s->device);
   for (int k = 0; k < 4; k++)
     if (s->graph[k]) cudaGraphExecDestroy(s->graph[k]);
-  float* f[] = {s->p, s->smoke, s->smoke_buf};
-  for (float* q : f)
-    if (q) cudaFree(q);
+  if (s->p) cudaFree(s->p);
+  if (s->smoke_block) cudaFree(s->smoke_block);  // smoke, smoke_buf
   if (s->vel_block) cudaFree(s->vel_block);  // u, v, u_buf, v_buf
   for (int k = 0; k < s->n_orders; k++)
     if (s->orders[k].order) cudaFree(s->orders[k].order);
@@ -234,11 +233,20 @@ static int create_impl(const sayal_config* c, int device, const sayal_slab* slab
     if (e != cudaSuccess) return fail(set_error(SAYAL_ECUDA, cudaGetErrorString(e)));
   }
   size_t bytes = field_elems(s) * sizeof(float);
-  float** fields[] = {&s->p, &s->smoke, &s->smoke_buf};
-  for (float** f : fields) {
-    e = cudaMalloc(f, bytes);
+  e = cudaMalloc(&s->p, bytes);
+  if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
+  cudaMemsetAsync(s->p, 0, bytes, s->stream);
+  // smoke and its back buffer: one allocation with a guard of one row + one cell before, between and behind the
+  // arrays.  advect_smoke_geo_kernel loads the four taps of a sample unconditionally and drops the closed ones by a
+  // select; with a base cell on the domain's border a closed tap's address lies up to one row + one cell outside.
+  {
+    const size_t guard = (((size_t)s->g.pitch + 1) * sizeof(float) + 255) & ~(size_t)255;
+    const size_t stride = ((bytes + 255) & ~(size_t)255) + guard;
+    e = cudaMalloc(&s->smoke_block, guard + 2 * stride);
     if (e != cudaSuccess) return fail(set_error(SAYAL_ENOMEM, cudaGetErrorString(e)));
-    cudaMemsetAsync(*f, 0, bytes, s->stream);
+    cudaMemsetAsync(s->smoke_block, 0, guard + 2 * stride, s->stream);
+    s->smoke = reinterpret_cast<float*>(reinterpret_cast<char*>(s->smoke_block) + guard);
+    s->smoke_buf = reinterpret_cast<float*>(reinterpret_cast<char*>(s->smoke_block) + guard + stride);
   }
   // u, v and their back buffers: one allocation (one IPC handle for a neighbouring slab), arrays 256-byte aligned
   s->vel_stride = (bytes + 255) & ~(size_t)255;

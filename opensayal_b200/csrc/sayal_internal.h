@@ -149,6 +149,7 @@ struct Sim {
   // them with one IPC handle and store its edge rows straight into our ghost rows (projection_pack.cu).
   float *u, *v, *p, *smoke, *u_buf, *v_buf, *smoke_buf;
   void* vel_block;
+  void* smoke_block;  // smoke, smoke_buf with guard rows around each (see create_impl)
   size_t vel_stride;
   uint8_t* flags;
   uint16_t* geo;                    // static per-cell geometry word of the tile advection (advect_tile.cu)
